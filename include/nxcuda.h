@@ -1,0 +1,189 @@
+/* nxcuda.h -- the C ABI of libnxcuda, the B200-native engine behind Nx's
+ * `nx.backend` seam.
+ *
+ * This is the drop-in boundary. An OCaml library `packages/nx-cuda`
+ * ((implements nx.backend)) binds these entry points 1:1 through OCaml
+ * externals, exactly as the reference's veneer binds its own C stubs
+ * (reference: packages/nx/lib/backend_c/nx_backend.ml:104-168, 242-264, 349,
+ * 482-483). Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions (all mirrored from the reference so the OCaml side is plumbing):
+ *   - dtype tags are Dtype.Packed.tag (reference: nx_c.h:130-168, 197-200).
+ *   - a tensor operand is {buffer, shape, strides, offset}, strides and offset
+ *     in ELEMENTS; strides may be 0 (broadcast) or negative (flip)
+ *     (reference: nx_c.h:47-61, 406-412).
+ *   - the OUTPUT is the first tensor argument and is allocated by the caller
+ *     (reference: nx_c_engine.h:256-262).
+ *   - a status is NULL on success, else a static never-freed string with the
+ *     same text as the reference's (reference: nx_c.h:378-388,
+ *     nx_c_engine.h:38-50). The binding raises "<op>: <status>" as
+ *     Invalid_argument when nxc_status_is_invalid_argument() says so, Failure
+ *     otherwise (reference: nx_c_engine.c:1345-1351).
+ *   - every launch is asynchronous on the context's stream; only nxc_sync and
+ *     nxc_d2h block. There is no CPU fallback anywhere in this library.
+ */
+#ifndef NXCUDA_H
+#define NXCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NXC_API __attribute__((visibility("default")))
+#else
+#define NXC_API
+#endif
+
+#define NXC_MAX_NDIM 32 /* reference: nx_c.h:45 */
+
+typedef const char *nxc_status; /* reference: nx_c.h:378-379 */
+#define NXC_OK ((nxc_status)0)
+
+/* Dtype.Packed.tag order (reference: nx_c.h:130-168). */
+typedef enum {
+  NXC_F16 = 0, NXC_F32 = 1, NXC_F64 = 2, NXC_BF16 = 3, NXC_F8E4M3 = 4,
+  NXC_F8E5M2 = 5, NXC_I4 = 6, NXC_U4 = 7, NXC_I8 = 8, NXC_U8 = 9, NXC_I16 = 10,
+  NXC_U16 = 11, NXC_I32 = 12, NXC_U32 = 13, NXC_I64 = 14, NXC_U64 = 15,
+  NXC_C32 = 16, NXC_C64 = 17, NXC_BOOL = 18, NXC_DTYPE_COUNT = 19
+} nxc_dtype;
+
+/* Operand descriptor; replaces the slots 0-3 the reference reads out of the
+   OCaml record (reference: nx_c.h:406-434). `data` is a DEVICE pointer to
+   element 0 of the buffer; the first live element is data + offset*elem_size. */
+typedef struct {
+  void *data;
+  int32_t dtype;
+  int32_t ndim;
+  int64_t shape[NXC_MAX_NDIM];
+  int64_t strides[NXC_MAX_NDIM];
+  int64_t offset;
+} nxc_tensor;
+
+/* Unary ops, in the reference's stub order (reference: nx_c_map.c:1184-1204). */
+typedef enum {
+  NXC_NEG = 0, NXC_RECIP, NXC_ABS, NXC_SIGN, NXC_SQRT, NXC_EXP, NXC_LOG, NXC_SIN,
+  NXC_COS, NXC_TAN, NXC_ASIN, NXC_ACOS, NXC_ATAN, NXC_SINH, NXC_COSH, NXC_TANH,
+  NXC_TRUNC, NXC_CEIL, NXC_FLOOR, NXC_ROUND, NXC_ERF, NXC_MAP1_COUNT
+} nxc_map1_op;
+
+/* Binary ops (reference: nx_c_map.c:1207-1221). */
+typedef enum {
+  NXC_ADD = 0, NXC_SUB, NXC_MUL, NXC_IDIV, NXC_FDIV, NXC_MOD, NXC_MAX, NXC_MIN,
+  NXC_POW, NXC_ATAN2, NXC_XOR, NXC_OR, NXC_AND, NXC_SHL, NXC_SHR, NXC_MAP2_COUNT
+} nxc_map2_op;
+
+/* Comparisons, bool output (reference: nx_c_map.c:1253-1256). */
+typedef enum { NXC_CMPEQ = 0, NXC_CMPNE, NXC_CMPLT, NXC_CMPLE, NXC_CMP_COUNT } nxc_cmp_op;
+
+/* Reductions / scans (reference: nx_c_fold.c:824-837). */
+typedef enum { NXC_SUM = 0, NXC_PROD, NXC_RMAX, NXC_RMIN, NXC_REDUCE_COUNT } nxc_reduce_op;
+
+typedef struct nxc_ctx nxc_ctx;
+
+/* ---- context, memory, transfer ------------------------------------------
+   replaces: `create_context : unit -> context` (reference:
+   backend/nx_backend.mli:32-39) and Nx_buffer.create / to_host / from_host
+   (reference: backend_c/nx_backend.ml:50-69). Device index comes from
+   NX_CUDA_DEVICE (default: LOCAL_RANK, else 0); matmul precision from
+   NX_CUDA_MATMUL in {f32 (default, exact), tf32}. */
+NXC_API nxc_status nxc_ctx_create(nxc_ctx **out);
+/* Same, on an explicit device and an existing cudaStream_t (NULL = own stream). */
+NXC_API nxc_status nxc_ctx_create_on(int device, void *cuda_stream, nxc_ctx **out);
+NXC_API void nxc_ctx_destroy(nxc_ctx *ctx);
+NXC_API nxc_status nxc_sync(nxc_ctx *ctx);
+NXC_API void *nxc_stream(nxc_ctx *ctx); /* the cudaStream_t launches go to */
+NXC_API int nxc_device(nxc_ctx *ctx);
+/* Detail text of the most recent non-OK status on this context (CUDA error
+   string included); never NULL. */
+NXC_API const char *nxc_last_error(nxc_ctx *ctx);
+/* Kernels launched by this library on this context since creation. */
+NXC_API uint64_t nxc_launch_count(nxc_ctx *ctx);
+/* 1 -> Invalid_argument, 0 -> Failure (reference: nx_c_engine.c:1345-1351,
+   nx_c_matmul.c:1229-1237). */
+NXC_API int nxc_status_is_invalid_argument(nxc_status s);
+NXC_API int64_t nxc_elem_size(int dtype); /* 0 for packed int4/uint4 (reference: nx_c.h:309-321) */
+NXC_API int nxc_set_matmul_mode(nxc_ctx *ctx, const char *mode); /* "f32" | "tf32"; 0 ok */
+
+NXC_API nxc_status nxc_alloc(nxc_ctx *ctx, size_t bytes, void **dptr); /* stream-ordered, cached */
+NXC_API nxc_status nxc_free(nxc_ctx *ctx, void *dptr);                 /* ordered after in-flight work */
+NXC_API nxc_status nxc_host_alloc(nxc_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+NXC_API nxc_status nxc_host_free(nxc_ctx *ctx, void *hptr);
+NXC_API nxc_status nxc_h2d(nxc_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
+NXC_API nxc_status nxc_d2h(nxc_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* blocks */
+NXC_API nxc_status nxc_memset(nxc_ctx *ctx, void *dst_dev, int byte, size_t bytes);
+
+/* ---- map family -----------------------------------------------------------
+   replaces caml_nx_c_{neg..erf}, caml_nx_c_{add..shr}, caml_nx_c_cmp*,
+   caml_nx_c_where, caml_nx_c_cast, caml_nx_c_copy (reference:
+   nx_c_map.c:1184-1280, nx_c_move.c:191-201) and Nx_buffer.fill as used by
+   `full` (reference: backend_c/nx_backend.ml:61-64). All operands carry
+   out->ndim dims of out->shape; input strides may be 0. */
+NXC_API nxc_status nxc_map1(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *a);
+NXC_API nxc_status nxc_map2(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *a,
+                    const nxc_tensor *b);
+NXC_API nxc_status nxc_cmp(nxc_ctx *ctx, int op, const nxc_tensor *out_bool, const nxc_tensor *a,
+                   const nxc_tensor *b);
+NXC_API nxc_status nxc_where(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *cond,
+                     const nxc_tensor *a, const nxc_tensor *b);
+NXC_API nxc_status nxc_cast(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a);
+NXC_API nxc_status nxc_copy(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a);
+/* `scalar` points at ONE element in out's storage type, on the HOST; it is
+   passed as a kernel argument (no H2D copy, no sync). */
+NXC_API nxc_status nxc_fill(nxc_ctx *ctx, const nxc_tensor *out, const void *scalar);
+
+/* ---- fold family ----------------------------------------------------------
+   replaces caml_nx_c_reduce_{sum,prod,max,min} and caml_nx_c_{argmax,argmin}
+   (reference: nx_c_fold.c:824-833, nx_c_engine.c:1052-1254, 1392-1473).
+   `axes` strictly increasing; `out` is either squeezed (rank in->ndim - n) or
+   full rank with size-1 reduced dims. argreduce writes int32. */
+NXC_API nxc_status nxc_reduce(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *in,
+                      const int *axes, int n_axes);
+NXC_API nxc_status nxc_argreduce(nxc_ctx *ctx, int is_max, const nxc_tensor *out_i32,
+                         const nxc_tensor *in, int axis);
+/* replaces caml_nx_c_cum{sum,prod,max,min} (reference: nx_c_fold.c:834-837). */
+NXC_API nxc_status nxc_scan(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *in, int axis);
+
+/* ---- matmul ---------------------------------------------------------------
+   replaces caml_nx_c_matmul (reference: nx_c_matmul.c:874-1108, 1271-1277).
+   A [...,m,k] and B [...,k,n] at arbitrary strides with broadcast batch dims;
+   out [batch...,m,n]. bf16/f16 run on tcgen05 tensor cores with f32
+   accumulation in TMEM; f32 is exact FFMA unless the context is in tf32 mode;
+   f64/int/complex/fp8 run on CUDA cores in the reference's compute type. */
+NXC_API nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a,
+                      const nxc_tensor *b);
+
+/* ---- move / index / random ("next" rows of the scope table) ----------------
+   replaces caml_nx_c_pad, _cat, _gather, _scatter, _threefry (reference:
+   nx_c_move.c:229-569, nx_c_random.c:44-140). */
+NXC_API nxc_status nxc_pad(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in,
+                   const void *fill_scalar_host, const int64_t *pad_before);
+NXC_API nxc_status nxc_cat(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *const *ins, int n_in,
+                   int axis);
+NXC_API nxc_status nxc_gather(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
+                      const nxc_tensor *indices_i32, int axis);
+/* `out` is pre-seeded with the template; mode 0 = Set (last write wins), 1 = Add. */
+NXC_API nxc_status nxc_scatter(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *indices_i32,
+                       const nxc_tensor *updates, int axis, int mode);
+NXC_API nxc_status nxc_threefry(nxc_ctx *ctx, const nxc_tensor *out_i32, const nxc_tensor *key_i32,
+                        const nxc_tensor *ctr_i32);
+
+/* ---- multi-GPU exchange (new; the reference has no collective in the
+   backend contract -- SURVEY.md section 8e). One process per GPU; NCCL is
+   dlopen'ed (libnccl.so.2) so the library loads without it. ------------------ */
+#define NXC_UNIQUE_ID_BYTES 128
+NXC_API nxc_status nxc_dist_unique_id(void *id_out_128);
+NXC_API nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const void *id_128);
+NXC_API nxc_status nxc_dist_finalize(nxc_ctx *ctx);
+/* In-place allreduce over `count` elements of `dtype`; op is an nxc_reduce_op. */
+NXC_API nxc_status nxc_allreduce(nxc_ctx *ctx, void *dev_buf, int64_t count, int dtype, int op);
+NXC_API nxc_status nxc_allgather(nxc_ctx *ctx, const void *dev_send, void *dev_recv,
+                         int64_t bytes_per_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NXCUDA_H */

@@ -1,0 +1,271 @@
+// nxc_common.cuh -- dtype traits, bit-exact storage<->compute converters, the
+// context, and launch helpers shared by every kernel family of libnxcuda.
+//
+// The dtype semantics implemented here are the reference's (nx_c.h:130-168,
+// 345-363; buffer/nx_buffer_stubs.h:73-302): f16/bf16/fp8 compute in float,
+// integers wrap on store, bool is 0/1. Integers are computed in their native
+// width on the device: every integer op the reference performs in a widened
+// 64-bit type and then wraps on store is a ring operation (or an order
+// operation on values that fit), so the native-width result is identical.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nxcuda.h"
+
+// ---- status strings (identical text to the reference) ----------------------
+#define NXC_ERR_NDIM "ndim exceeds NX_C_MAX_NDIM"
+#define NXC_ERR_RANK_MISMATCH "shape and strides rank disagree"
+#define NXC_ERR_BAD_KIND "unsupported bigarray kind"
+#define NXC_ERR_UNSUPPORTED_DTYPE "dtype not supported for this operation"
+#define NXC_ERR_PACKED "packed dtype not supported for this operation"
+#define NXC_ERR_SHAPE "shape mismatch"
+#define NXC_ERR_EMPTY_REDUCE "reduction over empty axis has no identity"
+#define NXC_ERR_ALLOC "out of memory"
+#define NXC_ERR_ARGREDUCE_CAP "argreduce axis length exceeds INT32_MAX"
+#define NXC_ERR_AXES "reduce axes must be strictly increasing and in range"
+#define NXC_ERR_OUT_RANK "output rank inconsistent with the operation"
+#define NXC_ERR_AXIS "axis out of range"
+#define NXC_ERR_OUT_ALIASED "output has a broadcast (zero) stride"
+#define NXC_ERR_ARITY "operand count exceeds NX_C_MAX_OPERANDS"
+#define NXC_ERR_DTYPE_MISMATCH "matmul operands must share one dtype"
+// new in this engine
+#define NXC_ERR_CUDA "CUDA error"
+#define NXC_ERR_NO_DEVICE "no CUDA device available (this backend has no CPU fallback)"
+#define NXC_ERR_NCCL "NCCL error"
+#define NXC_ERR_BAD_OP "unknown operation code"
+#define NXC_ERR_INDEX_DTYPE "indices must be int32"
+
+struct nxc_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int sm_count;
+  uint64_t launches;
+  int matmul_tf32;
+  char err[512];
+  // scratch for two-pass reductions (grown on demand, stream-ordered)
+  void *scratch;
+  size_t scratch_bytes;
+  // NCCL (dlopen'ed), see nxc_dist.cu
+  void *nccl_comm;
+  int rank, world;
+  // TMA descriptor encoder (driver entry point fetched at runtime)
+  void *encode_tiled;
+};
+
+nxc_status nxc_cuda_fail(nxc_ctx *ctx, cudaError_t e, const char *what);
+nxc_status nxc_scratch(nxc_ctx *ctx, size_t bytes, void **out);
+
+#define NXC_CUDA_TRY(ctx, expr)                                   \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return nxc_cuda_fail((ctx), _e, #expr); \
+  } while (0)
+
+#define NXC_LAUNCH_CHECK(ctx)                                            \
+  do {                                                                   \
+    (ctx)->launches++;                                                   \
+    cudaError_t _e = cudaPeekAtLastError();                              \
+    if (_e != cudaSuccess) return nxc_cuda_fail((ctx), _e, "kernel launch"); \
+  } while (0)
+
+// ---- dtype classes ---------------------------------------------------------
+enum { NXC_CLS_SINT = 1, NXC_CLS_UINT = 2, NXC_CLS_FLOAT = 4, NXC_CLS_COMPLEX = 8,
+       NXC_CLS_BOOL = 16, NXC_CLS_PACKED = 32 };
+
+static inline int nxc_dtype_class(int dt) {
+  switch (dt) {
+    case NXC_F16: case NXC_F32: case NXC_F64: case NXC_BF16: case NXC_F8E4M3: case NXC_F8E5M2:
+      return NXC_CLS_FLOAT;
+    case NXC_I4: return NXC_CLS_SINT | NXC_CLS_PACKED;
+    case NXC_U4: return NXC_CLS_UINT | NXC_CLS_PACKED;
+    case NXC_I8: case NXC_I16: case NXC_I32: case NXC_I64: return NXC_CLS_SINT;
+    case NXC_U8: case NXC_U16: case NXC_U32: case NXC_U64: return NXC_CLS_UINT;
+    case NXC_C32: case NXC_C64: return NXC_CLS_COMPLEX;
+    case NXC_BOOL: return NXC_CLS_BOOL;
+    default: return 0;
+  }
+}
+static inline bool nxc_is_packed(int dt) { return (nxc_dtype_class(dt) & NXC_CLS_PACKED) != 0; }
+static inline bool nxc_valid_dtype(int dt) { return dt >= 0 && dt < NXC_DTYPE_COUNT; }
+
+// ---- complex value types ---------------------------------------------------
+struct __align__(8) cf32 { float re, im; };
+struct __align__(16) cf64 { double re, im; };
+
+// ---- storage tags: distinct C++ types for dtypes that share a machine type --
+struct f16_s { uint16_t b; };
+struct bf16_s { uint16_t b; };
+struct f8e4_s { uint8_t b; };
+struct f8e5_s { uint8_t b; };
+struct bool_s { uint8_t b; };
+
+// ---- converters (bit-exact with buffer/nx_buffer_stubs.h) ---------------------
+__host__ __device__ inline uint32_t nxc_f2u(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } x; x.f = f; return x.u;
+#endif
+}
+__host__ __device__ inline float nxc_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } x; x.u = u; return x.f;
+#endif
+}
+
+// half -> float. NaNs are quieted and keep their payload (nx_buffer_stubs.h:150-182).
+__device__ inline float nxc_half_to_float(uint16_t h) {
+  if ((h & 0x7FFFu) > 0x7C00u)
+    return __uint_as_float(((uint32_t)(h & 0x8000u) << 16) | 0x7F800000u |
+                           ((uint32_t)(h & 0x3FFu) << 13) | 0x400000u);
+  return __half2float(__ushort_as_half(h));
+}
+// float -> half, RNE; a NaN keeps its top payload bits (nx_buffer_stubs.h:99-148).
+__device__ inline uint16_t nxc_float_to_half(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) {
+    uint16_t r = (uint16_t)(0x7C00u + ((b & 0x007FFFFFu) >> 13));
+    r += (r == 0x7C00u);
+    return (uint16_t)(((b & 0x80000000u) >> 16) + r);
+  }
+  return __half_as_ushort(__float2half_rn(f));
+}
+__device__ inline float nxc_bf16_to_float(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+// float -> bfloat16, RNE, NaN quieted keeping the sign (nx_buffer_stubs.h:73-86).
+__device__ inline uint16_t nxc_float_to_bf16(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((b >> 16) | 0x0040u);
+  return (uint16_t)((b + (((b >> 16) & 1u) + 0x7FFFu)) >> 16);
+}
+// Generic small-float encoder: EB exponent bits, MB mantissa bits, RNE with
+// subnormals. `maxbits` is the first magnitude pattern that means overflow and
+// `ovf` what overflow turns into (e4m3fn: NaN 0x7F; e5m2: Inf 0x7C)
+// (nx_buffer_stubs.h:189-223, 244-278).
+template <int EB, int MB, int BIAS, uint32_t MAXBITS, uint32_t OVF, uint32_t NANB, uint32_t INFB>
+__device__ inline uint8_t nxc_float_to_fp8(float f) {
+  uint32_t b = __float_as_uint(f);
+  uint32_t sign = (b >> 31) << 7;
+  uint32_t mag = b & 0x7FFFFFFFu;
+  if (mag > 0x7F800000u) return (uint8_t)NANB;          // NaN: sign dropped
+  if (mag == 0x7F800000u) return (uint8_t)(sign | INFB);
+  int exp = (int)((b >> 23) & 0xFF) - 127;
+  const int emin = 1 - BIAS;
+  if (exp >= emin) {
+    uint32_t sig = b & 0x7FFFFFu;
+    const int sh = 23 - MB;
+    uint32_t q = sig >> sh;
+    uint32_t rem = sig & ((1u << sh) - 1u);
+    uint32_t half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (q & 1u))) q++;
+    uint32_t bits = ((uint32_t)(exp + BIAS) << MB) + q;
+    if (bits >= MAXBITS) return (uint8_t)(sign | OVF);
+    return (uint8_t)(sign | bits);
+  }
+  uint32_t sig = (b & 0x7FFFFFu) | 0x800000u;
+  int shift = (23 - MB) + (emin - exp);
+  if (shift > 24) return (uint8_t)sign;
+  uint32_t q = sig >> shift;
+  uint32_t rem = sig & ((1u << shift) - 1u);
+  uint32_t half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) q++;
+  return (uint8_t)(sign | q);
+}
+__device__ inline uint8_t nxc_float_to_e4m3(float f) {
+  return nxc_float_to_fp8<4, 3, 7, 0x7Fu, 0x7Fu, 0x7Fu, 0x7Fu>(f);
+}
+__device__ inline uint8_t nxc_float_to_e5m2(float f) {
+  return nxc_float_to_fp8<5, 2, 15, 0x7Cu, 0x7Cu, 0x7Fu, 0x7Cu>(f);
+}
+// e4m3fn -> float: no infinities, S.1111.111 is (positive, quiet) NaN
+// (nx_buffer_stubs.h:225-240).
+__device__ inline float nxc_e4m3_to_float(uint8_t v) {
+  uint32_t e = (v >> 3) & 0xFu, m = v & 7u;
+  if (e == 0xFu && m == 7u) return __uint_as_float(0x7FC00000u);
+  float r = (e == 0) ? ldexpf((float)m, -9) : ldexpf(1.0f + (float)m * 0.125f, (int)e - 7);
+  return (v & 0x80u) ? -r : r;
+}
+__device__ inline float nxc_e5m2_to_float(uint8_t v) {
+  uint32_t e = (v >> 2) & 0x1Fu, m = v & 3u;
+  if (e == 0x1Fu) {
+    if (m == 0) return (v & 0x80u) ? -INFINITY : INFINITY;
+    return __uint_as_float(0x7FC00000u);
+  }
+  float r = (e == 0) ? ldexpf((float)m * 0.25f, -14) : ldexpf(1.0f + (float)m * 0.25f, (int)e - 15);
+  return (v & 0x80u) ? -r : r;
+}
+
+// ---- dtype traits ------------------------------------------------------------
+// S = storage type, C = compute type, cls = category.
+template <int DT> struct DT_;
+#define NXC_DEF_DT(tag, S_, C_, cls_, LD, ST)                         \
+  template <> struct DT_<tag> {                                       \
+    typedef S_ S;                                                     \
+    typedef C_ C;                                                     \
+    static constexpr int cls = cls_;                                  \
+    static constexpr int tag_ = tag;                                  \
+    __device__ static inline C ld(S s) { return LD; }                 \
+    __device__ static inline S st(C v) { return ST; }                 \
+  };
+NXC_DEF_DT(NXC_F16, f16_s, float, NXC_CLS_FLOAT, nxc_half_to_float(s.b), (f16_s{nxc_float_to_half(v)}))
+NXC_DEF_DT(NXC_F32, float, float, NXC_CLS_FLOAT, s, v)
+NXC_DEF_DT(NXC_F64, double, double, NXC_CLS_FLOAT, s, v)
+NXC_DEF_DT(NXC_BF16, bf16_s, float, NXC_CLS_FLOAT, nxc_bf16_to_float(s.b), (bf16_s{nxc_float_to_bf16(v)}))
+NXC_DEF_DT(NXC_F8E4M3, f8e4_s, float, NXC_CLS_FLOAT, nxc_e4m3_to_float(s.b), (f8e4_s{nxc_float_to_e4m3(v)}))
+NXC_DEF_DT(NXC_F8E5M2, f8e5_s, float, NXC_CLS_FLOAT, nxc_e5m2_to_float(s.b), (f8e5_s{nxc_float_to_e5m2(v)}))
+NXC_DEF_DT(NXC_I8, int8_t, int32_t, NXC_CLS_SINT, (int32_t)s, (int8_t)v)
+NXC_DEF_DT(NXC_U8, uint8_t, uint32_t, NXC_CLS_UINT, (uint32_t)s, (uint8_t)v)
+NXC_DEF_DT(NXC_I16, int16_t, int32_t, NXC_CLS_SINT, (int32_t)s, (int16_t)v)
+NXC_DEF_DT(NXC_U16, uint16_t, uint32_t, NXC_CLS_UINT, (uint32_t)s, (uint16_t)v)
+NXC_DEF_DT(NXC_I32, int32_t, int32_t, NXC_CLS_SINT, s, v)
+NXC_DEF_DT(NXC_U32, uint32_t, uint32_t, NXC_CLS_UINT, s, v)
+NXC_DEF_DT(NXC_I64, int64_t, int64_t, NXC_CLS_SINT, s, v)
+NXC_DEF_DT(NXC_U64, uint64_t, uint64_t, NXC_CLS_UINT, s, v)
+NXC_DEF_DT(NXC_C32, cf32, cf32, NXC_CLS_COMPLEX, s, v)
+NXC_DEF_DT(NXC_C64, cf64, cf64, NXC_CLS_COMPLEX, s, v)
+NXC_DEF_DT(NXC_BOOL, bool_s, uint32_t, NXC_CLS_BOOL, (uint32_t)(s.b != 0), (bool_s{(uint8_t)(v != 0)}))
+#undef NXC_DEF_DT
+
+// Dispatch a runtime dtype tag to a template instantiation over the 17 compute
+// dtypes. BODY sees `DT` as a constexpr int.
+#define NXC_DISPATCH_DTYPE(dt, ...)                                             \
+  switch (dt) {                                                                  \
+    case NXC_F16: { constexpr int DT = NXC_F16; __VA_ARGS__ } break;                    \
+    case NXC_F32: { constexpr int DT = NXC_F32; __VA_ARGS__ } break;                    \
+    case NXC_F64: { constexpr int DT = NXC_F64; __VA_ARGS__ } break;                    \
+    case NXC_BF16: { constexpr int DT = NXC_BF16; __VA_ARGS__ } break;                  \
+    case NXC_F8E4M3: { constexpr int DT = NXC_F8E4M3; __VA_ARGS__ } break;              \
+    case NXC_F8E5M2: { constexpr int DT = NXC_F8E5M2; __VA_ARGS__ } break;              \
+    case NXC_I8: { constexpr int DT = NXC_I8; __VA_ARGS__ } break;                      \
+    case NXC_U8: { constexpr int DT = NXC_U8; __VA_ARGS__ } break;                      \
+    case NXC_I16: { constexpr int DT = NXC_I16; __VA_ARGS__ } break;                    \
+    case NXC_U16: { constexpr int DT = NXC_U16; __VA_ARGS__ } break;                    \
+    case NXC_I32: { constexpr int DT = NXC_I32; __VA_ARGS__ } break;                    \
+    case NXC_U32: { constexpr int DT = NXC_U32; __VA_ARGS__ } break;                    \
+    case NXC_I64: { constexpr int DT = NXC_I64; __VA_ARGS__ } break;                    \
+    case NXC_U64: { constexpr int DT = NXC_U64; __VA_ARGS__ } break;                    \
+    case NXC_C32: { constexpr int DT = NXC_C32; __VA_ARGS__ } break;                    \
+    case NXC_C64: { constexpr int DT = NXC_C64; __VA_ARGS__ } break;                    \
+    case NXC_BOOL: { constexpr int DT = NXC_BOOL; __VA_ARGS__ } break;                  \
+    default: break;                                                              \
+  }
+
+// ---- host-side operand validation (reference: nx_c.h:420-434) ------------------
+static inline nxc_status nxc_check_tensor(const nxc_tensor *t) {
+  if (t->ndim < 0 || t->ndim > NXC_MAX_NDIM) return NXC_ERR_NDIM;
+  if (!nxc_valid_dtype(t->dtype)) return NXC_ERR_BAD_KIND;
+  return NXC_OK;
+}
+static inline int64_t nxc_numel(const nxc_tensor *t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; i++) n *= t->shape[i];
+  return n;
+}

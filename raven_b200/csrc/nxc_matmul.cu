@@ -1,0 +1,66 @@
+// nxc_matmul.cu -- C-ABI matmul entry: validate, resolve batch broadcast, route.
+// Replaces caml_nx_c_matmul and its driver's checks (reference:
+// nx_c_matmul.c:874-936, 1229-1277): same shape rules, same statuses
+// (shape/aliased -> Invalid_argument; dtype mismatch / unsupported -> Failure).
+#include "nxc_matmul.cuh"
+
+extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_tensor *A,
+                                 const nxc_tensor *B) {
+  nxc_status s = NXC_OK;
+  NxcMatmulProblem p;
+  if ((s = nxc_check_tensor(A)) || (s = nxc_check_tensor(B)) || (s = nxc_check_tensor(C))) goto fail;
+  if (A->dtype != B->dtype || A->dtype != C->dtype) { s = NXC_ERR_DTYPE_MISMATCH; goto fail; }
+  {
+    const int dt = A->dtype;
+    const int cls = nxc_dtype_class(dt);
+    if (cls & NXC_CLS_PACKED) { s = NXC_ERR_PACKED; goto fail; }
+    if (cls & NXC_CLS_BOOL) { s = NXC_ERR_UNSUPPORTED_DTYPE; goto fail; }
+    if (A->ndim < 2 || B->ndim < 2) { s = NXC_ERR_SHAPE; goto fail; }
+    const int nd = A->ndim > B->ndim ? A->ndim : B->ndim;
+    if (C->ndim != nd) { s = NXC_ERR_SHAPE; goto fail; }
+    p.dt = dt;
+    p.m = A->shape[A->ndim - 2];
+    p.k = A->shape[A->ndim - 1];
+    p.n = B->shape[B->ndim - 1];
+    if (p.k != B->shape[B->ndim - 2]) { s = NXC_ERR_SHAPE; goto fail; }
+    if (C->shape[nd - 2] != p.m || C->shape[nd - 1] != p.n) { s = NXC_ERR_SHAPE; goto fail; }
+    p.batch_nd = nd - 2;
+    p.nbatch = 1;
+    const int a_bo = nd - A->ndim, b_bo = nd - B->ndim;
+    for (int i = 0; i < p.batch_nd; i++) {
+      int64_t sa = 1, sb = 1, sta = 0, stb = 0;
+      if (i >= a_bo) { sa = A->shape[i - a_bo]; sta = A->strides[i - a_bo]; }
+      if (i >= b_bo) { sb = B->shape[i - b_bo]; stb = B->strides[i - b_bo]; }
+      if (sa != sb && sa != 1 && sb != 1) { s = NXC_ERR_SHAPE; goto fail; }
+      const int64_t sz = sa > sb ? sa : sb;
+      if (C->shape[i] != sz) { s = NXC_ERR_SHAPE; goto fail; }
+      p.bshape[i] = sz;
+      p.as_[i] = (sa == 1) ? 0 : sta;
+      p.bs_[i] = (sb == 1) ? 0 : stb;
+      p.cs_[i] = C->strides[i];
+      if (sz > 1 && p.cs_[i] == 0) { s = NXC_ERR_OUT_ALIASED; goto fail; }
+      p.nbatch *= sz;
+    }
+    if (p.m == 0 || p.n == 0 || p.nbatch == 0) return NXC_OK;
+    p.a_rs = A->strides[A->ndim - 2]; p.a_cs = A->strides[A->ndim - 1];
+    p.b_rs = B->strides[B->ndim - 2]; p.b_cs = B->strides[B->ndim - 1];
+    p.c_rs = C->strides[nd - 2]; p.c_cs = C->strides[nd - 1];
+    if ((p.m > 1 && p.c_rs == 0) || (p.n > 1 && p.c_cs == 0)) { s = NXC_ERR_OUT_ALIASED; goto fail; }
+    const int64_t es = nxc_elem_size(dt);
+    p.a = (const char *)A->data + A->offset * es;
+    p.b = (const char *)B->data + B->offset * es;
+    p.c = (char *)C->data + C->offset * es;
+
+    const bool tc_dtype = (dt == NXC_BF16 || dt == NXC_F16 || (dt == NXC_F32 && ctx->matmul_tf32));
+    if (tc_dtype) {
+      s = nxc_matmul_tc(ctx, p);
+      if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
+    }
+    s = nxc_matmul_simt(ctx, p);
+    if (s) goto fail;
+    return NXC_OK;
+  }
+fail:
+  if (s && strcmp(s, NXC_ERR_CUDA) != 0) snprintf(ctx->err, sizeof ctx->err, "%s", s);
+  return s;
+}

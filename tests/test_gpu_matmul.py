@@ -1,0 +1,120 @@
+"""GPU parity of matmul against the oracle through the C ABI: every compute dtype,
+transposed lhs / rhs / both, offsets, batched and batch-broadcast operands
+(backend_contract.ml:1932-2023, backend_c/test/matmul_test.ml:68-140 fills).
+
+Tolerances: integers bit-exact (accumulation is modular); f64 1e-11*(k+1) and f32
+1e-5*(k+1) relative to the row/column magnitude as the contract states; bf16/f16
+on the tcgen05 path 1e-3 relative against an f32-accumulated product of the same
+stored inputs plus one storage rounding (north_star).
+"""
+import numpy as np
+import pytest
+
+import raven_b200.backend as B
+from raven_b200 import Failure, InvalidArgument
+from tests import harness as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _fill(dtype, m, k, n):
+    """The reference's deterministic fills: fa i p = sin((i*k+p)*13 mod 1009), fb p j =
+    cos((p*n+j)*7 mod 1013) (matmul_test.ml:68-140)."""
+    i, p = np.meshgrid(np.arange(m), np.arange(k), indexing="ij")
+    fa = np.sin(((i * k + p) * 13) % 1009)
+    p2, j = np.meshgrid(np.arange(k), np.arange(n), indexing="ij")
+    fb = np.cos(((p2 * n + j) * 7) % 1013)
+    if dtype in H.INTS:
+        fa, fb = np.round(fa * 50), np.round(fb * 50)
+        if dtype in H.UINTS:
+            fa, fb = np.abs(fa), np.abs(fb)
+        return fa.astype(np.int64).astype(H.np_storage(dtype)), fb.astype(np.int64).astype(H.np_storage(dtype))
+    if dtype in H.COMPLEX:
+        return ((fa + 1j * fb[:m, :k] if fb.shape == fa.shape else fa + 0.5j * fa[::-1]).astype(H.np_storage(dtype)),
+                (fb - 0.25j * fb[::-1]).astype(H.np_storage(dtype)))
+    return H.to_storage(dtype, fa), H.to_storage(dtype, fb)
+
+
+def _tol(dtype, k):
+    if dtype == "f64" or dtype == "c64":
+        return 1e-11 * (k + 1)
+    if dtype == "f32" or dtype == "c32":
+        return 1e-5 * (k + 1) ** 0.5
+    return {"f16": 2e-3, "bf16": 1.6e-2, "f8e4m3": 0.13, "f8e5m2": 0.26}[dtype]
+
+
+def _check(ctx, oracle, dtype, a, b, what, k):
+    want = oracle.matmul(a, b).numpy()
+    got = H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, b)))
+    if dtype in H.INTS:
+        H.assert_same(dtype, got, want, what=what)
+    else:
+        scale = float(np.max(np.abs(H.storage_to_float(dtype, want) if dtype not in H.COMPLEX else want))) or 1.0
+        H.assert_close(dtype, got, want, rel=_tol(dtype, k), abs_=_tol(dtype, k) * scale, what=what)
+
+
+ALL = list(H.FLOATS) + list(H.INTS) + list(H.COMPLEX)
+
+
+@pytest.mark.parametrize("dtype", ALL)
+def test_matmul_layouts(ctx, oracle, dtype):
+    for (m, k, n) in [(5, 7, 3), (1, 1, 1), (64, 64, 64), (70, 33, 129)]:
+        A, Bm = _fill(dtype, m, k, n)
+        a = H.HostView(A.reshape(-1).copy(), dtype, [m, k])
+        b = H.HostView(Bm.reshape(-1).copy(), dtype, [k, n])
+        at = H.HostView(np.ascontiguousarray(A.T).reshape(-1), dtype, [k, m]).permute([1, 0])
+        bt = H.HostView(np.ascontiguousarray(Bm.T).reshape(-1), dtype, [n, k]).permute([1, 0])
+        for name, (x, y) in {"nn": (a, b), "tn": (at, b), "nt": (a, bt), "tt": (at, bt)}.items():
+            _check(ctx, oracle, dtype, x, y, f"matmul/{dtype}/{m}x{k}x{n}/{name}", k)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64", "i32", "bf16", "f16", "c32"])
+def test_matmul_batched(ctx, oracle, dtype):
+    m, k, n = 9, 17, 6
+    A, Bm = _fill(dtype, 4 * m, k, n)
+    a = H.HostView(A.reshape(-1).copy(), dtype, [2, 2, m, k])
+    b = H.HostView(Bm.reshape(-1).copy(), dtype, [k, n])
+    _check(ctx, oracle, dtype, a, b, f"batched-rhs2d/{dtype}", k)
+    A2, B2 = _fill(dtype, m, k, 6 * n)
+    b3 = H.HostView(np.ascontiguousarray(B2.reshape(k, 6, n).transpose(1, 0, 2)).reshape(-1), dtype, [3, 2, k, n])
+    a1 = H.HostView(A2.reshape(-1).copy(), dtype, [1, 1, m, k]).expand([3, 1, m, k])
+    _check(ctx, oracle, dtype, a1, b3, f"batch-broadcast/{dtype}", k)
+    # offset slice of A
+    big = H.HostView(A.reshape(-1).copy(), dtype, [4 * m, k]).shrink([(3, 3 + m), (2, k)])
+    bs = H.HostView(Bm.reshape(-1).copy(), dtype, [k, n]).shrink([(2, k), (0, n)])
+    _check(ctx, oracle, dtype, big, bs, f"offset/{dtype}", k - 2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16", "f64", "i32"])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 384, 640), (1024, 1024, 1024), (300, 4100, 200)])
+def test_matmul_large(ctx, oracle, dtype, shape):
+    m, k, n = shape
+    if dtype in ("f64", "i32") and m * k * n > 512 * 384 * 640:
+        pytest.skip("oracle too slow at this size for this dtype")
+    rng = np.random.default_rng(0)
+    if dtype in H.INTS:
+        A = rng.integers(-100, 100, (m, k)).astype(np.int32)
+        Bm = rng.integers(-100, 100, (k, n)).astype(np.int32)
+    else:
+        A = H.to_storage(dtype, rng.standard_normal((m, k)) / np.sqrt(k))
+        Bm = H.to_storage(dtype, rng.standard_normal((k, n)))
+    a = H.HostView(A.reshape(-1).copy(), dtype, [m, k])
+    b = H.HostView(Bm.reshape(-1).copy(), dtype, [k, n])
+    at = H.HostView(np.ascontiguousarray(A.T).reshape(-1), dtype, [k, m]).permute([1, 0])
+    bt = H.HostView(np.ascontiguousarray(Bm.T).reshape(-1), dtype, [n, k]).permute([1, 0])
+    for name, (x, y) in {"nn": (a, b), "tn": (at, b), "nt": (a, bt)}.items():
+        _check(ctx, oracle, dtype, x, y, f"matmul/{dtype}/{shape}/{name}", k)
+
+
+def test_matmul_errors(ctx):
+    from raven_b200 import dtype as D
+    a = B.buffer(ctx, D.float32, [3, 4])
+    b = B.buffer(ctx, D.float32, [5, 6])
+    with pytest.raises(InvalidArgument, match="matmul: shape mismatch"):
+        B.matmul(a, b)
+    x = B.buffer(ctx, D.bool_, [2, 2])
+    with pytest.raises(Failure, match="matmul: dtype not supported for this operation"):
+        B.matmul(x, x)
+    # k == 0 is a real zero fill
+    z = B.matmul(B.buffer(ctx, D.float32, [3, 0]), B.buffer(ctx, D.float32, [0, 2]))
+    assert (H.download(z) == 0).all()
