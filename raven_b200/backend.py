@@ -21,6 +21,7 @@ after in-flight kernels (cudaFreeAsync on the context stream).
 """
 from __future__ import annotations
 
+import builtins as _b
 import ctypes
 
 import numpy as np
@@ -155,7 +156,7 @@ def to_host(t: Tensor) -> np.ndarray:
     result is the flat buffer; index it with the view's offset/strides, as the
     frontend does (frontend.ml:1703-1708). Blocks until the stream drains."""
     n = t.buffer.nbytes
-    host = np.empty(n // max(t.dtype.np.itemsize, 1), dtype=t.dtype.np)
+    host = np.empty(n // _b.max(t.dtype.np.itemsize, 1), dtype=t.dtype.np)
     if n:
         check(t.context.ptr, "to_host",
               t.context._lib.nxc_d2h(t.context.ptr, host.ctypes.data, t.buffer.ptr, host.nbytes))
@@ -353,7 +354,7 @@ def pad(x: Tensor, padding, fill_value) -> Tensor:
     out = _create(x.context, dt, out_shape)
     scalar = np.zeros(1, dtype=dt.np)
     scalar[0] = fill_value
-    before = (ctypes.c_int64 * max(len(padding), 1))(*[b for b, _ in padding])
+    before = (ctypes.c_int64 * _b.max(len(padding), 1))(*[b for b, _ in padding])
     do, dx = out._desc(), x._desc()
     _call(x.context, "pad", x.context._lib.nxc_pad, ctypes.byref(do), ctypes.byref(dx),
           scalar.ctypes.data, before)
@@ -418,7 +419,7 @@ def reduce(x: Tensor, op: str, axes) -> Tensor:  # noqa: A001  (`reduce ~op ~axe
                 raise InvalidArgument(f"reduce_{op}: reduction over an empty axis has no identity")
     out = _create(x.context, x.dtype, reduce_output_shape(x.shape, axes, False))
     do, dx = out._desc(), x._desc()
-    ax = (ctypes.c_int * max(len(axes), 1))(*axes)
+    ax = (ctypes.c_int * _b.max(len(axes), 1))(*axes)
     _call(x.context, "reduce_" + op, x.context._lib.nxc_reduce, REDUCE_OPS[op], ctypes.byref(do),
           ctypes.byref(dx), ax, len(axes))
     return out

@@ -180,6 +180,11 @@ def download(t) -> np.ndarray:
     return B.to_numpy(t)
 
 
+def raw(x: np.ndarray) -> np.ndarray:
+    """The bytes of an array (works for 0-d too)."""
+    return np.ascontiguousarray(x).reshape(-1).view(np.uint8)
+
+
 # ---- comparison ------------------------------------------------------------------------------
 def ulp_diff(dtype: str, got: np.ndarray, want: np.ndarray) -> np.ndarray:
     """Distance in units in the last place of the STORAGE type; NaN vs NaN is 0,
@@ -221,10 +226,12 @@ def assert_same(dtype: str, got: np.ndarray, want: np.ndarray, ulp: float = 0, w
     if dtype in COMPLEX:
         part = "f32" if dtype == "c32" else "f64"
         rt = np.float32 if dtype == "c32" else np.float64
-        g = np.ascontiguousarray(got).view(rt)
-        w = np.ascontiguousarray(want).view(rt)
+        g = np.ascontiguousarray(got).reshape(-1).view(rt)
+        w = np.ascontiguousarray(want).reshape(-1).view(rt)
         # error relative to the modulus: a tiny component next to a large one carries the large one's ulp
-        mod = np.repeat(np.abs(want).reshape(-1), 2).reshape(g.shape).astype(np.float64)
+        with np.errstate(all="ignore"):
+            mod = np.repeat(np.abs(want).reshape(-1), 2).astype(np.float64)
+        mod = np.where(np.isfinite(mod), mod, 0.0)
         eps = np.finfo(rt).eps
         err = np.abs(g.astype(np.float64) - w.astype(np.float64))
         ok = (err <= max(ulp, 1) * eps * np.maximum(mod, np.finfo(rt).tiny)) | (np.isnan(g) & np.isnan(w)) | (g == w)

@@ -1,0 +1,165 @@
+"""Pins the oracle before anything trusts it.
+
+oracle/nxo.c (the C restatement) is compared, op by op, with the reference's own
+C backend compiled unmodified from /root/reference (oracle/_ref/libnxref.so) over
+the reference contract suite's pools and layout matrix
+(packages/nx/test/backend_contract.ml:125-289, 423-468, 555-593): every unary,
+binary and comparison op x every dtype x every layout (including which
+(op, dtype) pairs are rejected, and with which exception class and message),
+where, the 17 x 17 cast matrix with the contract's edge cases, copy/assign,
+reductions over axes [0] / [last] / all, argmax/argmin with keepdims, matmul
+over transposed / batched / broadcast operands.
+
+Bit-exact everywhere except: float sum/prod (reassociation; 4 ulp of the compute
+type) and complex transcendentals (libm vs libm: identical here, both are glibc).
+Skipped when oracle/_ref has not been built (it needs /root/reference).
+"""
+import numpy as np
+import pytest
+
+from oracle import nxo, ref
+from tests import harness as H
+
+pytestmark = pytest.mark.skipif(not (ref.available() and nxo.available()),
+                                reason="oracle/_ref/libnxref.so or oracle/libnxo.so not built")
+
+ALL = list(H.FLOATS) + list(H.INTS) + list(H.COMPLEX) + ["bool"]
+
+
+def _both(fn):
+    out = []
+    for m in (ref, nxo):
+        try:
+            out.append(fn(m))
+        except (ref.RefError, nxo.RefError) as e:
+            out.append(("err", e.kind, e.msg))
+    return out
+
+
+def _same(dt, r, o, what, ulp=0):
+    if isinstance(r, tuple) or isinstance(o, tuple):
+        assert r == o, f"{what}: reference {r} vs restatement {o}"
+        return False
+    x, y = o.numpy(), r.numpy()
+    if np.array_equal(H.raw(x), H.raw(y)):
+        return True
+    H.assert_same(dt, x, y, ulp=ulp, what=what)  # NaN payload / sign-of-zero differences only
+    return True
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_unary_matches_reference(dt):
+    for op in ref.UNARY:
+        for name, hv in H.layouts(dt):
+            r, o = _both(lambda m: m.unary(op, hv))
+            if not _same(dt, r, o, f"{op}/{dt}/{name}"):
+                break
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_binary_and_compare_match_reference(dt):
+    la, lb = dict(H.layouts(dt)), dict(H.layouts(dt, rot=5))
+    for op in ref.BINARY + ["shl", "shr"]:
+        for na, nb in H.BINARY_LAYOUT_PAIRS:
+            r, o = _both(lambda m: m.binary(op, la[na], lb[nb]))
+            if not _same(dt, r, o, f"{op}/{dt}/{na},{nb}"):
+                break
+    for op in ref.CMP:
+        for na, nb in H.BINARY_LAYOUT_PAIRS:
+            r, o = _both(lambda m: m.compare(op, la[na], lb[nb]))
+            if not _same("bool", r, o, f"{op}/{dt}/{na},{nb}"):
+                break
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_where_copy_assign_match_reference(dt):
+    la, lb, lc = dict(H.layouts(dt)), dict(H.layouts(dt, rot=7)), dict(H.layouts("bool", rot=2))
+    for nc, na, nb in [("contig", "contig", "contig"), ("transpose", "transpose", "transpose"),
+                       ("broadcast", "flip", "slice"), ("scalar", "scalar", "scalar"), ("empty", "empty", "empty")]:
+        r, o = _both(lambda m: m.where(lc[nc], la[na], lb[nb]))
+        _same(dt, r, o, f"where/{dt}/{nc}")
+    for name, hv in H.layouts(dt):
+        r, o = _both(lambda m: m.copy(hv))
+        _same(dt, r, o, f"copy/{dt}/{name}")
+    res = []
+    for m in (ref, nxo):
+        base = H.HostView(H.pool(dt, 18).copy(), dt, [3, 6])
+        m.assign(base.shrink([(0, 3), (1, 5)]).flip([0]), la["transpose"])
+        res.append(base.storage.copy())
+    assert np.array_equal(H.raw(res[0]), H.raw(res[1]))
+
+
+@pytest.mark.parametrize("src", ALL)
+def test_cast_matrix_matches_reference(src):
+    from tests.test_gpu_map import _cast_inputs
+    data = _cast_inputs(src)
+    n = (data.size // 2) * 2
+    for dst in ALL:
+        for hv in (H.HostView(data.copy(), src, [data.size]),
+                   H.HostView(data[:n].copy(), src, [n // 2, 2]).permute([1, 0])):
+            r, o = _both(lambda m: m.cast(hv, dst))
+            _same(dst, r, o, f"cast {src}->{dst}")
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_reduce_and_argreduce_match_reference(dt):
+    for op in ("sum", "prod", "max", "min"):
+        for name, hv in H.layouts(dt):
+            nd = len(hv.shape)
+            for axes in ([[]] if nd == 0 else [[0], [nd - 1], list(range(nd))]):
+                r, o = _both(lambda m: m.reduce(op, hv, axes))
+                exact = dt in H.INTS or dt == "bool" or op in ("max", "min")
+                _same(dt, r, o, f"{op}/{dt}/{name}/{axes}", ulp=0 if exact else 4)
+    if dt in H.COMPLEX:
+        return
+    for op in ("argmax", "argmin"):
+        for name, hv in H.layouts(dt, include_degenerate=False):
+            for axis in (0, len(hv.shape) - 1):
+                for keep in (False, True):
+                    r, o = _both(lambda m: m.argreduce(op, hv, axis, keep))
+                    _same("i32", r, o, f"{op}/{dt}/{name}/{axis}")
+    for op in ("sum", "prod", "max", "min"):
+        for name, hv in H.layouts(dt, include_degenerate=False):
+            r, o = _both(lambda m: m.scan(op, hv, len(hv.shape) - 1))
+            exact = dt in H.INTS or dt == "bool" or op in ("max", "min")
+            _same(dt, r, o, f"cum{op}/{dt}/{name}", ulp=0 if exact else 4)
+
+
+@pytest.mark.parametrize("dt", [d for d in ALL if d != "bool"])
+def test_matmul_matches_reference(dt):
+    from tests.test_gpu_matmul import _fill
+    for (m, k, n) in [(5, 7, 3), (1, 1, 1), (16, 9, 24)]:
+        A, B = _fill(dt, m, k, n)
+        a = H.HostView(A.reshape(-1).copy(), dt, [m, k])
+        b = H.HostView(B.reshape(-1).copy(), dt, [k, n])
+        at = H.HostView(np.ascontiguousarray(A.T).reshape(-1), dt, [k, m]).permute([1, 0])
+        bt = H.HostView(np.ascontiguousarray(B.T).reshape(-1), dt, [n, k]).permute([1, 0])
+        for x, y in ((a, b), (at, b), (a, bt), (at, bt)):
+            r, o = _both(lambda mod: mod.matmul(x, y))
+            if dt in H.INTS:
+                _same(dt, r, o, f"matmul/{dt}")
+            else:
+                H.assert_close(dt, o.numpy(), r.numpy(), rel=1e-5 if dt not in ("f64", "c64") else 1e-12,
+                               abs_=1e-5 if dt not in ("f64", "c64") else 1e-12, what=f"matmul/{dt}")
+
+
+def test_large_random_arrays_match_reference():
+    rng = np.random.default_rng(1)
+    n = 1 << 16
+    x = H.HostView(rng.uniform(-20, 20, n).astype(np.float32), "f32", [n])
+    y = H.HostView(rng.uniform(-20, 20, n).astype(np.float32), "f32", [n])
+    for op in ref.UNARY:
+        r, o = _both(lambda m: m.unary(op, x))
+        _same("f32", r, o, op)
+    for op in ("add", "mul", "fdiv", "pow", "atan2", "mod", "idiv", "max"):
+        r, o = _both(lambda m: m.binary(op, x, y))
+        _same("f32", r, o, op)
+    m2 = H.HostView(x.storage, "f32", [256, 256])
+    for axes in ([0], [1], [0, 1]):
+        r, o = _both(lambda m: m.reduce("sum", m2, axes))
+        H.assert_close("f32", o.numpy(), r.numpy(), rel=2e-6, abs_=1e-4, what=f"sum {axes}")
+        r, o = _both(lambda m: m.reduce("max", m2.permute([1, 0]), axes))
+        _same("f32", r, o, f"max {axes}")
+        if len(axes) == 1:
+            r, o = _both(lambda m: m.argreduce("argmin", m2.flip([0]), axes[0]))
+            _same("i32", r, o, f"argmin {axes}")
