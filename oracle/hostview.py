@@ -127,6 +127,8 @@ class HostView:
                         [self.strides[a] for a in axes], self.offset)
 
     def expand(self, shape):
+        if len(self.shape) == 0:  # a scalar expands to any shape (core/view.ml:86-89)
+            return HostView(self.storage, self.dtype, shape, [0] * len(shape), self.offset)
         st = [0 if (s == 1 and t != 1) else k for s, t, k in zip(self.shape, shape, self.strides)]
         return HostView(self.storage, self.dtype, shape, st, self.offset)
 

@@ -1,3 +1,458 @@
-// placeholder until the tcgen05 path lands (next commit)
+// nxc_matmul_tc.cu -- the tensor-core GEMM: tcgen05.mma with the accumulator in
+// TMEM, operands staged in shared memory by TMA, one persistent CTA per SM.
+//
+// Serves bf16 and f16 (f32 accumulate, the reference's "f16/bf16 compute in float"
+// rule, nx_c_matmul.c:12-28) and f32 in the opt-in tf32 mode. It replaces the
+// reference's pack -> microkernel -> store pipeline (nx_c_matmul.c:363-454,
+// 531-587) for those dtypes: "packing through arbitrary strides" becomes a TMA
+// tensor map over the view, so a transposed operand (what Rune's backward
+// produces, reverse.ml:585-654) is consumed in place:
+//
+//   operand view            TMA box (inner x outer)      UMMA smem layout
+//   A[m,k], a_cs == 1       K(128 B) x 128 rows          K-major,  SWIZZLE_128B
+//   A[m,k], a_rs == 1       M(128 B) x BLOCK_K rows, xN   MN-major, SWIZZLE_128B
+//   B[k,n], b_rs == 1       K(128 B) x 256 rows          K-major
+//   B[k,n], b_cs == 1       N(128 B) x BLOCK_K rows, xN   MN-major
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected thread) and
+// TMEM owner, warps 2-5 epilogue (tcgen05.ld -> convert -> 16-byte global stores).
+// Three pipelines: smem full/empty (4 stages x 48 KB), TMEM full/empty (two
+// 128x256 f32 accumulators = all 512 columns, so the epilogue of tile i overlaps
+// the MMAs of tile i+1), and a static persistent tile schedule that walks N
+// within groups of 8 M-blocks so concurrently resident tiles share A and B in L2.
+#include <cuda.h>
+
 #include "nxc_matmul.cuh"
-nxc_status nxc_matmul_tc(nxc_ctx *, const NxcMatmulProblem &) { return NXC_MM_TC_DECLINED; }
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int ROW_BYTES = 128;  // one swizzle row: BLOCK_K * esize
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+  int64_t m, n, k;
+  int64_t nbatch;
+  int64_t c_rs, c_bs;     // element strides of C (row, batch); column stride is 1
+  int num_m, num_n, num_kb;
+  int esize;              // operand element bytes (2 or 4)
+  int block_k;            // elements per k-block = 128 / esize
+  int a_mn, b_mn;         // operand is MN-major
+  int a_batched, b_batched;
+  uint32_t idesc;
+  int out_f32;            // C is f32 (tf32 mode) else 16-bit
+  int out_bf16;           // 16-bit flavour
+  int vec_store;          // rows of C are 16-byte aligned
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version bit)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version for Blackwell
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((b >> 16) | 0x0040u);
+  return (uint16_t)((b + (((b >> 16) & 1u) + 0x7FFFu)) >> 16);
+}
+__device__ __forceinline__ uint16_t f32_to_f16_rn(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) {
+    uint16_t r = (uint16_t)(0x7C00u + ((b & 0x007FFFFFu) >> 13));
+    r += (r == 0x7C00u);
+    return (uint16_t)(((b & 0x80000000u) >> 16) + r);
+  }
+  return __half_as_ushort(__float2half_rn(f));
+}
+
+__device__ __forceinline__ void tile_coords(const TcParams &p, int64_t t, int &bi, int &mb, int &nb) {
+  const int64_t per_batch = (int64_t)p.num_m * p.num_n;
+  bi = (int)(t / per_batch);
+  int r = (int)(t - (int64_t)bi * per_batch);
+  const int GROUP = 8;
+  const int per_group = GROUP * p.num_n;
+  const int g = r / per_group;
+  const int first_m = g * GROUP;
+  const int gsz = (p.num_m - first_m) < GROUP ? (p.num_m - first_m) : GROUP;
+  const int rr = r - g * per_group;
+  mb = first_m + rr % gsz;
+  nb = rr / gsz;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 void *__restrict__ Cout, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t total_tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int elems_per_row = ROW_BYTES / p.esize;  // elements in one 128-byte swizzle row
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int bi, mb, nb;
+        tile_coords(p, t, bi, mb, nb);
+        const int m0 = mb * BLOCK_M, n0 = nb * BLOCK_N;
+        const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
+        for (int kb = 0; kb < p.num_kb; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          const int k0 = kb * p.block_k;
+          uint8_t *sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t *sb = smem_b + stage * B_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_3d(&map_a, &full[stage], sa, k0, m0, ba);
+          } else {
+            const int box_bytes = p.block_k * ROW_BYTES;
+            for (int j = 0; j < BLOCK_M / elems_per_row; j++)
+              tma_load_3d(&map_a, &full[stage], sa + j * box_bytes, m0 + j * elems_per_row, k0, ba);
+          }
+          if (!p.b_mn) {
+            tma_load_3d(&map_b, &full[stage], sb, k0, n0, bb);
+          } else {
+            const int box_bytes = p.block_k * ROW_BYTES;
+            for (int j = 0; j < BLOCK_N / elems_per_row; j++)
+              tma_load_3d(&map_b, &full[stage], sb + j * box_bytes, n0 + j * elems_per_row, k0, bb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint32_t box_bytes = (uint32_t)p.block_k * ROW_BYTES;
+    // K-major: 8-row groups 1024 B apart, a k-step is 32 B inside the swizzle row.
+    // MN-major: atoms of 128 B x 8 k-rows, next MN atom one TMA box away, a k-step is
+    // (32 / esize) k-rows = that many 128-byte rows.
+    const uint32_t a_lbo = p.a_mn ? box_bytes : 16, a_sbo = 1024;
+    const uint32_t b_lbo = p.b_mn ? box_bytes : 16, b_sbo = 1024;
+    const uint32_t kstep_rows = 32 / p.esize;
+    const uint32_t a_kstep = p.a_mn ? kstep_rows * ROW_BYTES : 32;
+    const uint32_t b_kstep = p.b_mn ? kstep_rows * ROW_BYTES : 32;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; kb++) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint64_t ad = make_desc(sa + j * a_kstep, a_lbo, a_sbo);
+            const uint64_t bd = make_desc(sb + j * b_kstep, b_lbo, b_sbo);
+            const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+            if (p.esize == 2) umma_f16(tmem_d, ad, bd, p.idesc, acc);
+            else umma_tf32(tmem_d, ad, bd, p.idesc, acc);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.num_kb == 0) {  // k == 0: nothing accumulates; the epilogue writes zeros
+        if (elect_one()) umma_commit(&tfull[as]);
+        __syncwarp();
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int bi, mb, nb;
+      tile_coords(p, t, bi, mb, nb);
+      mbar_wait(&tfull[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = (int64_t)mb * BLOCK_M + q * 32 + lane;
+      const int64_t col0 = (int64_t)nb * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BLOCK_N;
+      const int64_t crow = (int64_t)bi * p.c_bs + row * p.c_rs;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; c++) {
+        uint32_t v[32];
+        if (p.num_kb > 0) {
+          tmem_ld32(taddr + c * 32, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = 0;
+        }
+        const int64_t col = col0 + c * 32;
+        if (row < p.m && col < p.n) {
+          if (p.out_f32) {
+            float *dst = (float *)Cout + crow + col;
+            if (p.vec_store && col + 32 <= p.n) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                *(uint4 *)(dst + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              for (int i = 0; i < 32 && col + i < p.n; i++) dst[i] = __uint_as_float(v[i]);
+            }
+          } else {
+            uint16_t h[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              h[i] = p.out_bf16 ? f32_to_bf16_rn(__uint_as_float(v[i])) : f32_to_f16_rn(__uint_as_float(v[i]));
+            uint16_t *dst = (uint16_t *)Cout + crow + col;
+            if (p.vec_store && col + 32 <= p.n) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint4 w;
+                w.x = h[8 * i] | ((uint32_t)h[8 * i + 1] << 16);
+                w.y = h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16);
+                w.z = h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16);
+                w.w = h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16);
+                *(uint4 *)(dst + 8 * i) = w;
+              }
+            } else {
+              for (int i = 0; i < 32 && col + i < p.n; i++) dst[i] = h[i];
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Build the 3-D tensor map (inner, outer, batch) of one operand.
+bool encode_operand(nxc_ctx *ctx, CUtensorMap *map, const void *base, CUtensorMapDataType dt, int esize,
+                    int64_t inner_extent, int64_t outer_extent, int64_t outer_stride_elems, int64_t nbatch,
+                    int64_t batch_stride_elems, int box_outer) {
+  EncodeTiledFn fn = (EncodeTiledFn)ctx->encode_tiled;
+  if (!fn) return false;
+  if (((uintptr_t)base & 15) != 0) return false;
+  const int64_t ob = outer_stride_elems * esize, bb = batch_stride_elems * esize;
+  if (ob <= 0 || (ob & 15) != 0) return false;
+  if (nbatch > 1 && (bb <= 0 || (bb & 15) != 0)) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent, (cuuint64_t)(nbatch > 1 ? nbatch : 1)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ob, (cuuint64_t)(nbatch > 1 ? bb : ob * outer_extent)};
+  if ((gstr[1] & 15) != 0) gstr[1] = (gstr[1] + 15) & ~(cuuint64_t)15;
+  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / esize), (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, dt, 3, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
+  if (!ctx->encode_tiled) return NXC_MM_TC_DECLINED;
+  const int esize = (q.dt == NXC_F32) ? 4 : 2;
+  if (q.k == 0 || q.m >= 0x7FFFFFFFLL || q.n >= 0x7FFFFFFFLL || q.k >= 0x7FFFFFFFLL) return NXC_MM_TC_DECLINED;
+  // tiny products are launch/latency bound on a 128x256 tile: leave them to the CUDA-core path
+  if (q.m * q.n * q.k < (int64_t)64 * 64 * 64) return NXC_MM_TC_DECLINED;
+  if (q.c_cs != 1) return NXC_MM_TC_DECLINED;
+
+  // batch dims must collapse to one stride per operand (or a full broadcast)
+  int64_t a_bs = 0, b_bs = 0, c_bs = 0;
+  bool a_b = false, b_b = false;
+  if (q.nbatch > 1) {
+    // walk from the innermost batch dim outwards, requiring composition
+    int64_t ext = 1;
+    bool first = true;
+    for (int i = q.batch_nd - 1; i >= 0; i--) {
+      if (q.bshape[i] == 1) continue;
+      if (first) { a_bs = q.as_[i]; b_bs = q.bs_[i]; c_bs = q.cs_[i]; first = false; }
+      else if (q.as_[i] != a_bs * ext || q.bs_[i] != b_bs * ext || q.cs_[i] != c_bs * ext) return NXC_MM_TC_DECLINED;
+      ext *= q.bshape[i];
+    }
+    a_b = a_bs != 0;
+    b_b = b_bs != 0;
+  }
+
+  TcParams p;
+  p.m = q.m; p.n = q.n; p.k = q.k; p.nbatch = q.nbatch;
+  p.c_rs = q.c_rs; p.c_bs = c_bs;
+  p.esize = esize;
+  p.block_k = ROW_BYTES / esize;
+  p.num_m = (int)((q.m + BLOCK_M - 1) / BLOCK_M);
+  p.num_n = (int)((q.n + BLOCK_N - 1) / BLOCK_N);
+  p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
+  p.a_batched = a_b; p.b_batched = b_b;
+  p.out_f32 = (q.dt == NXC_F32);
+  p.out_bf16 = (q.dt == NXC_BF16);
+  p.vec_store = (((uintptr_t)q.c & 15) == 0) && ((q.c_rs * esize) % 16 == 0) && ((c_bs * esize) % 16 == 0);
+
+  // operand majors
+  if (q.a_cs == 1 || q.k == 1) p.a_mn = 0;
+  else if (q.a_rs == 1 || q.m == 1) p.a_mn = 1;
+  else return NXC_MM_TC_DECLINED;
+  if (q.b_rs == 1 || q.k == 1) p.b_mn = 0;
+  else if (q.b_cs == 1 || q.n == 1) p.b_mn = 1;
+  else return NXC_MM_TC_DECLINED;
+  // a K-major operand needs a real row stride; degenerate extents fall back
+  if ((q.k == 1 && q.a_cs != 1) || (q.k == 1 && q.b_rs != 1)) return NXC_MM_TC_DECLINED;
+  if ((p.a_mn && q.a_rs != 1) || (p.b_mn && q.b_cs != 1)) return NXC_MM_TC_DECLINED;
+
+  const CUtensorMapDataType tdt = q.dt == NXC_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                  : q.dt == NXC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMap map_a, map_b;
+  bool ok;
+  if (!p.a_mn) ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.k, q.m, q.a_rs, a_b ? q.nbatch : 1, a_bs, BLOCK_M);
+  else ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.m, q.k, q.a_cs, a_b ? q.nbatch : 1, a_bs, p.block_k);
+  if (!ok) return NXC_MM_TC_DECLINED;
+  if (!p.b_mn) ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.k, q.n, q.b_cs, b_b ? q.nbatch : 1, b_bs, BLOCK_N);
+  else ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.n, q.k, q.b_rs, b_b ? q.nbatch : 1, b_bs, p.block_k);
+  if (!ok) return NXC_MM_TC_DECLINED;
+
+  // instruction descriptor: D = f32, A/B format, majors, N >> 3, M >> 4
+  const uint32_t fmt = q.dt == NXC_BF16 ? 1u : q.dt == NXC_F16 ? 0u : 2u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
+  const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  nxc_mm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
+  NXC_LAUNCH_CHECK(ctx);
+  return NXC_OK;
+}

@@ -57,8 +57,12 @@ def test_unary_layouts(ctx, oracle, op, dtype):
         r = _run_both(lambda: oracle.unary(op, hv), lambda: getattr(B, op)(H.upload(ctx, hv)))
         if r[0] == "err":
             return
-        cplx = dtype in H.COMPLEX
-        H.assert_same(dtype, H.download(r[2]), r[1].numpy(), ulp=(8 if cplx else _ulp(dtype, op in EXACT_UNARY)),
+        if dtype in H.COMPLEX and op not in ("neg", "abs"):
+            # complex: the contract's tolerance (backend_contract.ml:2329-2382), relative to the modulus
+            tol = 1e-5 if dtype == "c32" else 1e-11
+            H.assert_close(dtype, H.download(r[2]), r[1].numpy(), rel=tol, abs_=tol, what=f"{op}/{dtype}/{name}")
+            continue
+        H.assert_same(dtype, H.download(r[2]), r[1].numpy(), ulp=_ulp(dtype, op in EXACT_UNARY),
                       what=f"{op}/{dtype}/{name}")
 
 
@@ -73,8 +77,11 @@ def test_binary_layouts(ctx, oracle, op, dtype):
                       lambda: getattr(B, BFN.get(op, op))(H.upload(ctx, a), H.upload(ctx, b)))
         if r[0] == "err":
             return
-        cplx = dtype in H.COMPLEX
-        H.assert_same(dtype, H.download(r[2]), r[1].numpy(), ulp=(8 if cplx else _ulp(dtype, op in EXACT_BINARY)),
+        if dtype in H.COMPLEX and op not in ("add", "sub"):
+            tol = 1e-5 if dtype == "c32" else 1e-11
+            H.assert_close(dtype, H.download(r[2]), r[1].numpy(), rel=tol, abs_=tol, what=f"{op}/{dtype}/{na},{nb}")
+            continue
+        H.assert_same(dtype, H.download(r[2]), r[1].numpy(), ulp=_ulp(dtype, op in EXACT_BINARY),
                       what=f"{op}/{dtype}/{na},{nb}")
 
 
