@@ -62,6 +62,8 @@ typedef const char *nxo_status;
 #define E_ALIASED "output has a broadcast (zero) stride"
 #define E_MM_DTYPE "matmul operands must share one dtype"
 #define E_BAD_OP "unknown operation code"
+#define E_INDEX_OOB "index out of bounds for the gathered/scattered axis" /* nx_c_move.c:49 */
+#define E_THREEFRY_SHAPE "threefry: last axis must have extent 2"             /* nx_c_random.c:32 */
 
 enum { F16, F32, F64, BF16, F8E4M3, F8E5M2, I4, U4, I8, U8, I16, U16, I32, U32, I64, U64, C32, C64, BOOL_, NDT };
 /* compute kinds = the reference's compute types (nx_c.h:130-168) */
@@ -946,13 +948,12 @@ nxo_status nxo_cat(const nxo_tensor *out, const nxo_tensor *const *ins, int n, i
   if (at != out->shape[axis]) return E_SHAPE;
   return NULL;
 }
-/* out[i...] = data[i... with coord[axis] = idx[i...]]; negative indices wrap once; out of
-   range is clamped (nx_c_move.c:342-442) */
-static int64_t norm_index(int64_t ix, int64_t len) {
-  if (ix < 0) ix += len;
-  if (ix < 0) ix = 0;
-  if (ix >= len) ix = len - 1;
-  return ix;
+/* out[c] = data[c with axis -> idx[c]]; indices are int32, Python-wrapped once, then
+   bounds-checked: an out-of-range index is an error, never clamped
+   (nx_c_move.c:342-362, 402-442) */
+static int norm_index(int64_t *ix, int64_t len) {
+  if (*ix < 0) *ix += len;
+  return *ix >= 0 && *ix < len;
 }
 nxo_status nxo_gather(const nxo_tensor *out, const nxo_tensor *data, const nxo_tensor *idx, int axis) {
   nxo_status s;
@@ -960,37 +961,47 @@ nxo_status nxo_gather(const nxo_tensor *out, const nxo_tensor *data, const nxo_t
   if (DT_CAT[out->dtype] & CAT_PACKED) return E_PACKED;
   if (axis < 0 || axis >= data->ndim) return E_AXIS;
   if (idx->ndim != data->ndim || out->ndim != data->ndim) return E_SHAPE;
+  for (int d = 0; d < out->ndim; d++) if (out->shape[d] != idx->shape[d]) return E_SHAPE;
   int64_t es = DT_SIZE[data->dtype], len = data->shape[axis];
   odo o;
   odo_init(&o, out->ndim, out->shape);
   odo_add(&o, out, NULL);
   odo_add(&o, idx, NULL);
   for (int64_t i = 0; i < o.total; i++, odo_next(&o)) {
+    int64_t ix = *(int32_t *)o.ptr[1];
+    if (!norm_index(&ix, len)) return E_INDEX_OOB;
     int64_t off = data->offset;
-    for (int d = 0; d < data->ndim; d++)
-      off += (d == axis ? norm_index(*(int32_t *)o.ptr[1], len) : o.coord[d]) * data->strides[d];
+    for (int d = 0; d < data->ndim; d++) off += (d == axis ? ix : o.coord[d]) * data->strides[d];
     memcpy(o.ptr[0], (const char *)data->data + off * es, (size_t)es);
   }
   return NULL;
 }
+/* `Set: the last write in row-major order wins; `Add accumulates in the compute type,
+   serially in row-major order (nx_c_move.c:444-569) */
 nxo_status nxo_scatter(const nxo_tensor *out, const nxo_tensor *idx, const nxo_tensor *upd, int axis, int mode) {
   nxo_status s;
   if ((s = chk(out)) || (s = chk(upd)) || (s = chk(idx))) return s;
   int dt = out->dtype;
   if (DT_CAT[dt] & CAT_PACKED) return E_PACKED;
   if (axis < 0 || axis >= out->ndim) return E_AXIS;
-  if (mode == 1 && (DT_CAT[dt] & CAT_BOOL)) return E_UNSUPPORTED;
+  if (out->ndim != idx->ndim || out->ndim != upd->ndim) return E_SHAPE;
+  for (int d = 0; d < out->ndim; d++) {
+    if (idx->shape[d] != upd->shape[d]) return E_SHAPE;
+    if (d != axis && idx->shape[d] != out->shape[d]) return E_SHAPE;
+  }
   int64_t es = DT_SIZE[dt], len = out->shape[axis];
   odo o;
   odo_init(&o, idx->ndim, idx->shape);
   odo_add(&o, idx, NULL);
   odo_add(&o, upd, NULL);
   for (int64_t i = 0; i < o.total; i++, odo_next(&o)) {
+    int64_t ix = *(int32_t *)o.ptr[0];
+    if (!norm_index(&ix, len)) return E_INDEX_OOB;
     int64_t off = out->offset;
-    for (int d = 0; d < out->ndim; d++)
-      off += (d == axis ? norm_index(*(int32_t *)o.ptr[0], len) : o.coord[d]) * out->strides[d];
+    for (int d = 0; d < out->ndim; d++) off += (d == axis ? ix : o.coord[d]) * out->strides[d];
     char *dst = (char *)out->data + off * es;
     if (mode == 0) memcpy(dst, o.ptr[1], (size_t)es);
+    else if (DT_KIND[dt] == K_BOOL) { val r; r.b = (uint8_t)((ld(dt, dst).b + ld(dt, o.ptr[1]).b) != 0); st(dt, dst, r); }
     else st(dt, dst, bin_apply(ADD, dt, ld(dt, dst), ld(dt, o.ptr[1])));
   }
   return NULL;
@@ -1020,8 +1031,11 @@ nxo_status nxo_threefry(const nxo_tensor *out, const nxo_tensor *key, const nxo_
   nxo_status s;
   if ((s = chk(out)) || (s = chk(key)) || (s = chk(ctr))) return s;
   if (out->dtype != I32 || key->dtype != I32 || ctr->dtype != I32) return E_UNSUPPORTED;
-  int nd = out->ndim;
-  if (nd < 1 || out->shape[nd - 1] != 2) return E_SHAPE;
+  int nd = key->ndim;
+  if (nd < 1 || nd != ctr->ndim || nd != out->ndim) return E_THREEFRY_SHAPE;
+  for (int d = 0; d < nd; d++)
+    if (key->shape[d] != ctr->shape[d] || key->shape[d] != out->shape[d]) return E_THREEFRY_SHAPE;
+  if (key->shape[nd - 1] != 2) return E_THREEFRY_SHAPE;
   odo o;
   odo_init(&o, nd - 1, out->shape);
   odo_add(&o, out, NULL);
@@ -1042,5 +1056,5 @@ nxo_status nxo_threefry(const nxo_tensor *out, const nxo_tensor *key, const nxo_
 int nxo_status_is_invalid_argument(nxo_status s) {
   if (!s) return 0;
   return !strcmp(s, E_EMPTY_REDUCE) || !strcmp(s, E_AXES) || !strcmp(s, E_AXIS) || !strcmp(s, E_OUT_RANK) ||
-         !strcmp(s, E_ALIASED) || !strcmp(s, E_SHAPE);
+         !strcmp(s, E_ALIASED) || !strcmp(s, E_SHAPE) || !strcmp(s, E_THREEFRY_SHAPE);
 }

@@ -192,8 +192,7 @@ def full(ctx: Context, dt, shape, value) -> Tensor:
     sync), so `x *. c`-style scalar operands cost one tiny launch."""
     dt = _dt.of(dt)
     t = _create(ctx, dt, shape)
-    scalar = np.zeros(1, dtype=dt.np)
-    scalar[0] = value
+    scalar = _dt.encode_scalar(dt, value)
     d = t._desc()
     check(ctx.ptr, "full", ctx._lib.nxc_fill(ctx.ptr, ctypes.byref(d), scalar.ctypes.data))
     return t
@@ -352,8 +351,7 @@ def pad(x: Tensor, padding, fill_value) -> Tensor:
     dt = x.dtype
     out_shape = [d + b + a for d, (b, a) in zip(x.shape, padding)]
     out = _create(x.context, dt, out_shape)
-    scalar = np.zeros(1, dtype=dt.np)
-    scalar[0] = fill_value
+    scalar = _dt.encode_scalar(dt, fill_value)
     before = (ctypes.c_int64 * _b.max(len(padding), 1))(*[b for b, _ in padding])
     do, dx = out._desc(), x._desc()
     _call(x.context, "pad", x.context._lib.nxc_pad, ctypes.byref(do), ctypes.byref(dx),

@@ -51,3 +51,58 @@ def of(x) -> Dtype:
     if isinstance(x, Dtype):
         return x
     return BY_NAME[x]
+
+
+def _fp8_encode(x: float, mb: int, bias: int, maxbits: int, ovf: int, infb: int) -> int:
+    """float -> fp8 bits, RNE with subnormals (reference: buffer/nx_buffer_stubs.h:189-278)."""
+    f = np.float32(x)
+    b = int(np.array([f], dtype=np.float32).view(np.uint32)[0])
+    if (b & 0x7FFFFFFF) > 0x7F800000:
+        return 0x7F
+    sign = (b >> 31) << 7
+    if (b & 0x7FFFFFFF) == 0x7F800000:
+        return sign | infb
+    ex = ((b >> 23) & 0xFF) - 127
+    emin = 1 - bias
+    if ex >= emin:
+        sh = 23 - mb
+        sig = b & 0x7FFFFF
+        q, rem, half = sig >> sh, sig & ((1 << sh) - 1), 1 << (sh - 1)
+        if rem > half or (rem == half and (q & 1)):
+            q += 1
+        bits = ((ex + bias) << mb) + q
+        return sign | (ovf if bits >= maxbits else bits)
+    shift = (23 - mb) + (emin - ex)
+    if shift > 24:
+        return sign
+    sig = (b & 0x7FFFFF) | 0x800000
+    q, rem, half = sig >> shift, sig & ((1 << shift) - 1), 1 << (shift - 1)
+    if rem > half or (rem == half and (q & 1)):
+        q += 1
+    return sign | q
+
+
+def encode_scalar(dt: Dtype, value) -> np.ndarray:
+    """One element of `dt` in its storage representation, from a Python number (the
+    `'a` of `full : context -> ('a,'b) Dtype.t -> int array -> 'a -> t`). Integers
+    already in storage form (numpy integer scalars for f16/bf16/fp8 bit patterns)
+    pass through unchanged."""
+    out = np.zeros(1, dtype=dt.np)
+    raw_bits = isinstance(value, (np.integer,)) and dt.name in ("f16", "bf16", "f8e4m3", "f8e5m2")
+    if dt.name == "f16" and not raw_bits:
+        out[0] = np.array([value], dtype=np.float16).view(np.uint16)[0]
+    elif dt.name == "bf16" and not raw_bits:
+        b = int(np.array([value], dtype=np.float32).view(np.uint32)[0])
+        out[0] = ((b >> 16) | 0x40) if (b & 0x7FFFFFFF) > 0x7F800000 else ((b + 0x7FFF + ((b >> 16) & 1)) >> 16) & 0xFFFF
+    elif dt.name == "f8e4m3" and not raw_bits:
+        out[0] = _fp8_encode(value, 3, 7, 0x7F, 0x7F, 0x7F)
+    elif dt.name == "f8e5m2" and not raw_bits:
+        out[0] = _fp8_encode(value, 2, 15, 0x7C, 0x7C, 0x7C)
+    elif dt.name == "bool":
+        out[0] = 1 if value else 0
+    elif dt.cls in ("sint", "uint"):
+        out[0] = np.array([int(value) & ((1 << (8 * dt.itemsize)) - 1)], dtype=np.uint64).astype(dt.np)[0] \
+            if not isinstance(value, np.generic) else value
+    else:
+        out[0] = value
+    return out

@@ -1,0 +1,143 @@
+"""Leading-axis sharded reductions, argreductions and batch-leading matmuls over
+several GPUs: one process per GPU, NCCL over NVLink 5 / NVSwitch for the one
+exchange step each of these paths has.
+
+The reference's backend contract has no collective (its only multi-device route
+is Rune.jit/pmap through tolk, reference: packages/rune/lib/jit.ml:181-212), so
+this module is new surface next to the `nx.backend` seam, not a replacement for
+reference code. What it must preserve is the single-device ANSWER:
+
+  reduce sum/prod   partial = local reduce of the slab; allreduce(sum/prod). Integer
+                    results are bit-identical (modular arithmetic is associative);
+                    float results differ from one device by one extra combine level
+                    (inside the 1e-5 relative bound).
+  reduce max/min    integers: allreduce(max/min). Floats: NCCL's max/min do not
+                    promise NaN propagation, and the reference's do (nx_c_fold.c:80-89),
+                    so the partials are allgathered and folded locally with the
+                    backend's own NaN-sticky max/min.
+  argmax/argmin     each rank emits (local extreme value, local index + slab offset);
+                    both are allgathered and the winner is chosen by the backend's own
+                    argreduce over the gathered values, ties and NaNs resolving to
+                    the lowest rank = the lowest global index, i.e. bit-exact.
+  axes not including the sharded axis -> outputs are disjoint: allgather only.
+  batch-leading matmul -> independent per rank; allgather of C only on request.
+
+`comm` is anything with rank / world / allreduce(tensor, op) / allgather(tensor);
+`NcclComm` is the product implementation over the C ABI (nxc_allreduce /
+nxc_allgather). Tests drive the same host logic with a gloo-backed comm on CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import backend as B
+from . import dtype as D
+from ._lib import check
+
+_OPS = {"sum": 0, "prod": 1, "max": 2, "min": 3}
+
+
+class NcclComm:
+    """NCCL communicator owned by the engine context (dlopen'ed libnccl). The
+    128-byte unique id is created on rank 0 and handed to the other ranks by
+    `exchange_id`, a callable rank0_bytes -> bytes (e.g. a torch.distributed
+    broadcast, an MPI bcast or a file)."""
+
+    def __init__(self, ctx: B.Context, rank: int, world: int, exchange_id):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        lib = ctx._lib
+        buf = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            check(ctx.ptr, "dist_unique_id", lib.nxc_dist_unique_id(buf))
+        ident = exchange_id(bytes(buf))
+        idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(ident)
+        check(ctx.ptr, "dist_init", lib.nxc_dist_init(ctx.ptr, self.rank, self.world, idbuf))
+
+    def allreduce(self, t: B.Tensor, op: str) -> B.Tensor:
+        """In place over a C-contiguous tensor."""
+        assert B.is_c_contiguous(t)
+        n = 1
+        for s in t.shape:
+            n *= s
+        check(self.ctx.ptr, "allreduce",
+              self.ctx._lib.nxc_allreduce(self.ctx.ptr, t.buffer.ptr, n, t.dtype.tag, _OPS[op]))
+        return t
+
+    def allgather(self, t: B.Tensor) -> B.Tensor:
+        """[world, *t.shape], rank-major."""
+        t = B.contiguous(t)
+        out = B.buffer(self.ctx, t.dtype, (self.world,) + tuple(t.shape))
+        nbytes = t.dtype.itemsize
+        for s in t.shape:
+            nbytes *= s
+        check(self.ctx.ptr, "allgather",
+              self.ctx._lib.nxc_allgather(self.ctx.ptr, t.buffer.ptr, out.buffer.ptr, nbytes))
+        return out
+
+    def close(self):
+        self.ctx._lib.nxc_dist_finalize(self.ctx.ptr)
+
+
+def slab_bounds(extent: int, rank: int, world: int):
+    """Equal leading-axis slabs; the last ranks take one element less when the extent
+    does not divide (first `extent % world` ranks get the extra one)."""
+    base, extra = divmod(extent, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sharded_reduce(x_local, op: str, axes, comm, backend=B):
+    """`reduce ~op ~axes` of the tensor whose axis-0 slabs live on the ranks."""
+    axes = sorted(int(a) for a in axes)
+    part = backend.reduce(x_local, op, axes)
+    if 0 not in axes:
+        g = comm.allgather(part)  # [world, slab, ...] -> concatenate slabs along axis 0
+        shp = tuple(g.shape)
+        return backend.reshape(g, (shp[0] * shp[1],) + shp[2:]) if len(shp) >= 2 else g
+    is_float = x_local.dtype.cls in ("float", "complex")
+    if op in ("max", "min") and is_float:
+        g = comm.allgather(part)  # NaN-sticky fold by the backend's own kernel
+        return backend.reduce(g, op, [0])
+    return comm.allreduce(backend.contiguous(part), op)
+
+
+def sharded_argreduce(x_local, is_max: bool, axis: int, slab_offset: int, comm, backend=B):
+    """argmax/argmin along `axis`; indices are global when axis == 0 is the sharded axis."""
+    fn = backend.argmax if is_max else backend.argmin
+    idx = fn(x_local, axis, False)
+    if axis != 0:
+        g = comm.allgather(idx)
+        shp = tuple(g.shape)
+        return backend.reshape(g, (shp[0] * shp[1],) + shp[2:]) if len(shp) >= 2 else g
+    val = backend.reduce(x_local, "max" if is_max else "min", [0])
+    # NaN-sticky max/min returns NaN exactly when the local argreduce picked a NaN: consistent
+    gidx = backend.add(idx, backend.expand(backend.full(idx.context, D.int32, [], int(slab_offset)), idx.shape)
+                       ) if len(idx.shape) else backend.add(idx, backend.full(idx.context, D.int32, [], int(slab_offset)))
+    gv = comm.allgather(val)    # [world, ...]
+    gi = comm.allgather(gidx)   # [world, ...]
+    win = fn(gv, 0, True)       # which rank wins, first-NaN / first-tie = lowest rank
+    out = backend.gather(gi, win, 0)
+    return backend.reshape(out, tuple(idx.shape))
+
+
+def sharded_batch_matmul(a_local, b_local, comm=None, gather: bool = False, backend=B):
+    """Independent per-rank products of a leading-batch slab; allgather C on request."""
+    c = backend.matmul(a_local, b_local)
+    if gather and comm is not None:
+        g = comm.allgather(c)
+        shp = tuple(g.shape)
+        return backend.reshape(g, (shp[0] * shp[1],) + shp[2:])
+    return c
+
+
+def allreduce_mean_(tensors, comm, backend=B):
+    """Data-parallel gradient averaging (the Kaun DP hook): sum-allreduce every
+    gradient leaf in place and scale by 1/world."""
+    out = []
+    for t in tensors:
+        t = backend.contiguous(t)
+        comm.allreduce(t, "sum")
+        inv = backend.expand(backend.full(t.context, t.dtype, [], 1.0 / comm.world), t.shape) if len(t.shape) \
+            else backend.full(t.context, t.dtype, [], 1.0 / comm.world)
+        out.append(backend.mul(t, inv))
+    return out

@@ -163,3 +163,49 @@ def test_large_random_arrays_match_reference():
         if len(axes) == 1:
             r, o = _both(lambda m: m.argreduce("argmin", m2.flip([0]), axes[0]))
             _same("i32", r, o, f"argmin {axes}")
+
+
+def test_move_and_random_match_reference():
+    """pad / cat / gather / scatter / threefry, including the
+    Random123 known-answer vectors the contract pins (backend_contract.ml:1663-1666)."""
+    rng = np.random.default_rng(4)
+    for dt in ("f32", "i32", "u8", "bf16", "c32", "bool", "i64"):
+        base = H.HostView(H.pool(dt, 18).copy(), dt, [3, 6])
+        views = {"contig": base, "T": H.HostView(H.pool(dt, 18).copy(), dt, [6, 3]).permute([1, 0]),
+                 "slice": H.HostView(np.tile(H.pool(dt, 18), 2).copy(), dt, [3, 12]).shrink([(0, 3), (2, 8)])}
+        fill = H.HostView(H.pool(dt, 18)[4:5].copy(), dt, [])
+        for name, v in views.items():
+            r, o = _both(lambda m: m.pad(v, [(1, 2), (0, 3)], fill))
+            _same(dt, r, o, f"pad/{dt}/{name}")
+            r, o = _both(lambda m: m.cat([v, views["contig"], v], 0))
+            _same(dt, r, o, f"cat0/{dt}/{name}")
+            r, o = _both(lambda m: m.cat([v, views["T"]], 1))
+            _same(dt, r, o, f"cat1/{dt}/{name}")
+            for axis, hi in ((0, 3), (1, 6)):
+                idx = H.HostView(rng.integers(-hi, hi, 4 * 5).astype(np.int32), "i32", [4, 5])
+                shape = [4, 6] if axis == 0 else [3, 5]
+                idx = H.HostView(rng.integers(-hi, hi, shape[0] * shape[1]).astype(np.int32), "i32", shape)
+                r, o = _both(lambda m: m.gather(v, idx, axis))
+                _same(dt, r, o, f"gather/{dt}/{name}/{axis}")
+                upd = H.HostView(np.resize(H.pool(dt, 18), shape[0] * shape[1]).copy(), dt, shape)
+                for mode in ("set", "add"):
+                    r, o = _both(lambda m: m.scatter(v, idx, upd, axis, mode))
+                    _same(dt, r, o, f"scatter-{mode}/{dt}/{name}/{axis}")
+        bad = H.HostView(np.array([0, 7, 1], dtype=np.int32), "i32", [1, 3]).expand([3, 3])
+        r, o = _both(lambda m: m.gather(base, H.HostView(np.array([0, 9, 1] * 6, dtype=np.int32), "i32", [3, 6]), 0))
+        assert isinstance(r, tuple) and r == o and r[1] == "Failure"
+    # threefry: the three Random123 KATs + random keys/counters over strided operands
+    def tf(m, k0, k1, c0, c1):
+        key = H.HostView(np.array([k0, k1], dtype=np.uint32).view(np.int32), "i32", [1, 2])
+        ctr = H.HostView(np.array([c0, c1], dtype=np.uint32).view(np.int32), "i32", [1, 2])
+        return m.threefry(key, ctr).numpy().reshape(-1).view(np.uint32).tolist()
+    for m in (ref, nxo):
+        assert tf(m, 0, 0, 0, 0) == [0x6b200159, 0x99ba4efe]
+        assert tf(m, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == [0x1cb996fc, 0xbb002be7]
+        assert tf(m, 0x13198a2e, 0x03707344, 0x243f6a88, 0x85a308d3) == [0xc4923a9c, 0x483df7a0]
+    key = H.HostView(rng.integers(-2**31, 2**31, 64, dtype=np.int64).astype(np.int32), "i32", [2, 32]).permute([1, 0])
+    ctr = H.HostView(rng.integers(-2**31, 2**31, 64, dtype=np.int64).astype(np.int32), "i32", [32, 2])
+    r, o = _both(lambda m: m.threefry(key, ctr))
+    _same("i32", r, o, "threefry")
+    r, o = _both(lambda m: m.threefry(H.HostView(np.zeros(6, np.int32), "i32", [2, 3]), H.HostView(np.zeros(6, np.int32), "i32", [2, 3])))
+    assert isinstance(r, tuple) and r == o and r[1] == "Invalid_argument", (r, o)
