@@ -207,8 +207,12 @@ def main():
     if dist:
         import torch.distributed as td
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy-default) stream shared by torch's events and the engine's launches
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = B.create_context(device=local, stream=stream.cuda_stream)
+    assert ctx.stream() == stream.cuda_stream
     comm = None
     if dist:
         def exchange(idbytes):

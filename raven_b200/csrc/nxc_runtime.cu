@@ -110,7 +110,8 @@ extern "C" int nxc_set_matmul_mode(nxc_ctx *ctx, const char *mode) {
 extern "C" int nxc_status_is_invalid_argument(nxc_status s) {
   if (!s) return 0;
   static const char *inv[] = {NXC_ERR_EMPTY_REDUCE, NXC_ERR_AXES, NXC_ERR_AXIS,
-                              NXC_ERR_OUT_RANK, NXC_ERR_OUT_ALIASED, NXC_ERR_SHAPE};
+                              NXC_ERR_OUT_RANK, NXC_ERR_OUT_ALIASED, NXC_ERR_SHAPE,
+                              "threefry: last axis must have extent 2"};
   for (size_t i = 0; i < sizeof inv / sizeof inv[0]; i++)
     if (strcmp(s, inv[i]) == 0) return 1;
   return 0;

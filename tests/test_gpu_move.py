@@ -1,0 +1,135 @@
+"""GPU parity of the "next" rows of the scope table:
+pad, cat, gather, scatter (Set last-wins / Add), threefry, cumulative scans --
+against the oracle through the C ABI. Everything here is bit-exact except float
+scatter-Add with duplicate targets (atomic order; 1e-5 relative) -- scans are
+sequential per slice on both sides, so even float scans are bit-identical.
+"""
+import numpy as np
+import pytest
+
+import raven_b200.backend as B
+from raven_b200 import Failure, InvalidArgument
+from tests import harness as H
+from tests.test_gpu_map import _rand
+
+pytestmark = pytest.mark.gpu
+
+DTS = ["f32", "f64", "i32", "u8", "bf16", "f16", "c32", "bool", "i64", "u16"]
+
+
+def _views(dt):
+    return {"contig": H.HostView(H.pool(dt, 18).copy(), dt, [3, 6]),
+            "T": H.HostView(H.pool(dt, 18).copy(), dt, [6, 3]).permute([1, 0]),
+            "slice": H.HostView(np.tile(H.pool(dt, 18), 2).copy(), dt, [3, 12]).shrink([(0, 3), (2, 8)])}
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_pad_cat(ctx, oracle, dt):
+    vs = _views(dt)
+    fill_hv = H.HostView(H.pool(dt, 18)[4:5].copy(), dt, [])
+    fill_val = H.pool(dt, 18)[4]
+    for name, v in vs.items():
+        for padding in ([(1, 2), (0, 3)], [(0, 0), (2, 0)], [(0, 0), (0, 0)]):
+            want = oracle.pad(v, padding, fill_hv).numpy()
+            got = H.download(B.pad(H.upload(ctx, v), padding, fill_val))
+            assert np.array_equal(H.raw(got), H.raw(want)), f"pad/{dt}/{name}/{padding}"
+        want = oracle.cat([v, vs["contig"], v], 0).numpy()
+        got = H.download(B.cat([H.upload(ctx, v), H.upload(ctx, vs["contig"]), H.upload(ctx, v)], 0))
+        assert np.array_equal(H.raw(got), H.raw(want)), f"cat0/{dt}/{name}"
+        want = oracle.cat([v, vs["T"]], 1).numpy()
+        got = H.download(B.cat([H.upload(ctx, v), H.upload(ctx, vs["T"])], -1))
+        assert np.array_equal(H.raw(got), H.raw(want)), f"cat1/{dt}/{name}"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_gather_scatter(ctx, oracle, dt):
+    rng = np.random.default_rng(4)
+    for name, v in _views(dt).items():
+        for axis, hi in ((0, 3), (1, 6)):
+            shape = [4, 6] if axis == 0 else [3, 5]
+            idx = H.HostView(rng.integers(-hi, hi, shape[0] * shape[1]).astype(np.int32), "i32", shape)
+            want = oracle.gather(v, idx, axis).numpy()
+            got = H.download(B.gather(H.upload(ctx, v), H.upload(ctx, idx), axis))
+            assert np.array_equal(H.raw(got), H.raw(want)), f"gather/{dt}/{name}/{axis}"
+            upd = H.HostView(np.resize(H.pool(dt, 18), shape[0] * shape[1]).copy(), dt, shape)
+            for mode in ("set", "add"):
+                want = oracle.scatter(v, idx, upd, axis, mode).numpy()
+                got = H.download(B.scatter(H.upload(ctx, v), H.upload(ctx, idx), H.upload(ctx, upd), axis, mode))
+                if mode == "add" and dt in H.FLOATS + H.COMPLEX:
+                    H.assert_close(dt, got, want, rel=3e-2 if dt in ("bf16", "f16") else 1e-5, abs_=1e-5,
+                                   what=f"scatter-add/{dt}/{name}/{axis}")
+                else:
+                    assert np.array_equal(H.raw(got), H.raw(want)), f"scatter-{mode}/{dt}/{name}/{axis}"
+    base = _views(dt)["contig"]
+    bad = H.HostView(np.array([0, 9, 1] * 6, dtype=np.int32), "i32", [3, 6])
+    with pytest.raises(Failure, match="gather: index out of bounds for the gathered/scattered axis"):
+        B.gather(H.upload(ctx, base), H.upload(ctx, bad), 0)
+
+
+def test_embedding_shaped_gather_and_scatter_add(ctx, oracle):
+    """take -> gather with a column-broadcast index, backward = scatter Add into zeros
+    (kaun/lib/embedding.ml, rune/lib/reverse.ml:521-526)."""
+    rng = np.random.default_rng(0)
+    V, Dm, T = 1000, 64, 4096
+    table = H.HostView(rng.standard_normal(V * Dm).astype(np.float32), "f32", [V, Dm])
+    ids = H.HostView(rng.integers(0, V, T).astype(np.int32), "i32", [T, 1]).expand([T, Dm])
+    want = oracle.gather(table, ids, 0).numpy()
+    got = H.download(B.gather(H.upload(ctx, table), H.upload(ctx, ids), 0))
+    assert np.array_equal(got, want)
+    g = H.HostView(rng.standard_normal(T * Dm).astype(np.float32), "f32", [T, Dm])
+    zeros = H.HostView(np.zeros(V * Dm, np.float32), "f32", [V, Dm])
+    want = oracle.scatter(zeros, ids, g, 0, "add").numpy()
+    got = H.download(B.scatter(H.upload(ctx, zeros), H.upload(ctx, ids), H.upload(ctx, g), 0, "add"))
+    H.assert_close("f32", got, want, rel=1e-5, abs_=1e-5, what="embedding backward")
+    gi = H.HostView(rng.integers(-1000, 1000, T * Dm).astype(np.int32), "i32", [T, Dm])
+    zi = H.HostView(np.zeros(V * Dm, np.int32), "i32", [V, Dm])
+    want = oracle.scatter(zi, ids, gi, 0, "add").numpy()
+    got = H.download(B.scatter(H.upload(ctx, zi), H.upload(ctx, ids), H.upload(ctx, gi), 0, "add"))
+    assert np.array_equal(got, want)
+    want = oracle.scatter(zi, ids, gi, 0, "set").numpy()  # many duplicates: last write must win
+    got = H.download(B.scatter(H.upload(ctx, zi), H.upload(ctx, ids), H.upload(ctx, gi), 0, "set"))
+    assert np.array_equal(got, want)
+
+
+def test_threefry(ctx, oracle):
+    def tf(k0, k1, c0, c1):
+        key = H.HostView(np.array([k0, k1], dtype=np.uint32).view(np.int32), "i32", [1, 2])
+        ctr = H.HostView(np.array([c0, c1], dtype=np.uint32).view(np.int32), "i32", [1, 2])
+        return H.download(B.threefry(H.upload(ctx, key), H.upload(ctx, ctr))).reshape(-1).view(np.uint32).tolist()
+    # Random123 known-answer vectors (backend_contract.ml:1663-1666)
+    assert tf(0, 0, 0, 0) == [0x6b200159, 0x99ba4efe]
+    assert tf(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == [0x1cb996fc, 0xbb002be7]
+    assert tf(0x13198a2e, 0x03707344, 0x243f6a88, 0x85a308d3) == [0xc4923a9c, 0x483df7a0]
+    rng = np.random.default_rng(2)
+    n = 1 << 16
+    key = H.HostView(rng.integers(-2**31, 2**31, 2 * n, dtype=np.int64).astype(np.int32), "i32", [2, n]).permute([1, 0])
+    ctr = H.HostView(rng.integers(-2**31, 2**31, 2 * n, dtype=np.int64).astype(np.int32), "i32", [n, 2])
+    want = oracle.threefry(key, ctr).numpy()
+    got = H.download(B.threefry(H.upload(ctx, key), H.upload(ctx, ctr)))
+    assert np.array_equal(got, want)
+    z = H.HostView(np.zeros(6, np.int32), "i32", [2, 3])
+    with pytest.raises(InvalidArgument, match="threefry: threefry: last axis must have extent 2"):
+        B.threefry(H.upload(ctx, z), H.upload(ctx, z))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "i32", "u8", "bf16", "i64", "bool", "c32"])
+@pytest.mark.parametrize("op", ["sum", "prod", "max", "min"])
+def test_scan(ctx, oracle, op, dt):
+    rng = np.random.default_rng(8)
+    cases = [hv for _, hv in H.layouts(dt, include_degenerate=False)]
+    data = H.to_storage(dt, rng.uniform(0.9, 1.1, 64 * 300)) if dt in H.FLOATS else _rand(dt, 64 * 300, rng)
+    big = H.HostView(data, dt, [64, 300])
+    cases += [big, big.permute([1, 0]), big.flip([1])]
+    for hv in cases:
+        for axis in range(len(hv.shape)):
+            try:
+                want = oracle.scan(op, hv, axis).numpy()
+            except Exception as e:
+                with pytest.raises(Failure):
+                    B.associative_scan(H.upload(ctx, hv), axis, op)
+                return
+            got = H.download(B.associative_scan(H.upload(ctx, hv), axis, op))
+            if dt in H.COMPLEX:
+                H.assert_close(dt, got, want, rel=1e-5, abs_=1e-5, what=f"cum{op}/{dt}")
+            else:
+                H.assert_same(dt, got, want, ulp=0, what=f"cum{op}/{dt}/{hv.shape}/{axis}")
