@@ -18,7 +18,14 @@ template <int IS_MAX, int DT> struct ArgP {
   static constexpr int cls = D::cls;
   static constexpr bool ok = (cls != NXC_CLS_COMPLEX);
   __device__ __forceinline__ static A identity() { A a; a.v = C(); a.idx = -1; return a; }
-  __device__ __forceinline__ static A make(S s, int64_t r) { A a; a.v = D::ld(s); a.idx = (int32_t)r; return a; }
+  // one element, visited in increasing index order per accumulator: a strict
+  // comparison keeps the first of equals, the NaN clause lets the first NaN win
+  __device__ __forceinline__ static void step(A &acc, S s, int64_t r) {
+    const C v = D::ld(s);
+    bool take = IS_MAX ? (v > acc.v) : (v < acc.v);
+    if constexpr (cls == NXC_CLS_FLOAT) take = take || ((v != v) && !(acc.v != acc.v));
+    if (take || acc.idx < 0) { acc.v = v; acc.idx = (int32_t)r; }
+  }
   __device__ __forceinline__ static A combine(A a, A b) {
     if (a.idx < 0) return b;
     if (b.idx < 0) return a;

@@ -114,7 +114,7 @@ template <int OP, int DT> struct RedP {
       return Lim<A, cls>::hi();
     }
   }
-  __device__ __forceinline__ static A make(S s, int64_t) { return D::ld(s); }
+  __device__ __forceinline__ static void step(A &acc, S s, int64_t) { acc = combine(acc, D::ld(s)); }
   __device__ __forceinline__ static A combine(A a, A b) {
     if constexpr (cls == NXC_CLS_COMPLEX) {
       return OP == NXC_SUM ? zadd(a, b) : zmul(a, b);

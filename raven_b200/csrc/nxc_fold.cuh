@@ -102,7 +102,8 @@ __device__ __forceinline__ A nxc_shfl_xor(const A &v, int mask) {
 // ---- row kernel ------------------------------------------------------------------
 // P: reduction policy with
 //   typedef S (input storage), A (accumulator), SO (output storage)
-//   static A identity(); static A make(S, int64_t r); static A combine(A, A);
+//   static A identity(); static void step(A&, S, int64_t r)  (r increases per accumulator);
+//   static A combine(A, A)  (order-free merge of partials);
 //   static SO finish(A)
 template <class P, int VEC>
 __global__ void __launch_bounds__(NXC_FOLD_THREADS)
@@ -143,14 +144,14 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
-          for (int j = 0; j < VEC; j++) acc[u] = P::combine(acc[u], P::make(v[u][j], r + u * step + j));
+          for (int j = 0; j < VEC; j++) P::step(acc[u], v[u][j], r + u * step + j);
       }
       for (; r < r1; r += step) {
         S v[VEC];
         if (VEC > 1) nxc_load_vec<S, VEC>(p + r, v);
         else v[0] = p[r * a.s_inner];
 #pragma unroll
-        for (int j = 0; j < VEC; j++) acc[0] = P::combine(acc[0], P::make(v[j], r + j));
+        for (int j = 0; j < VEC; j++) P::step(acc[0], v[j], r + j);
       }
     } else {
       for (; r < r1; r += step) {
@@ -164,7 +165,7 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
         if (VEC > 1) nxc_load_vec<S, VEC>(p, v);
         else v[0] = p[0];
 #pragma unroll
-        for (int j = 0; j < VEC; j++) acc[0] = P::combine(acc[0], P::make(v[j], r + j));
+        for (int j = 0; j < VEC; j++) P::step(acc[0], v[j], r + j);
       }
     }
   }
@@ -223,13 +224,13 @@ nxc_fold_lane_kernel(const typename P::S *__restrict__ in, typename P::SO *__res
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
-          for (int j = 0; j < VEC; j++) acc[j] = P::combine(acc[j], P::make(v[u][j], r + u * TY));
+          for (int j = 0; j < VEC; j++) P::step(acc[j], v[u][j], r + u * TY);
       }
       for (; r < r1; r += TY) {
         S v[VEC];
         nxc_load_vec<S, VEC>(p + r * rs, v);
 #pragma unroll
-        for (int j = 0; j < VEC; j++) acc[j] = P::combine(acc[j], P::make(v[j], r));
+        for (int j = 0; j < VEC; j++) P::step(acc[j], v[j], r);
       }
     } else {
       for (; r < r1; r += TY) {
@@ -238,7 +239,7 @@ nxc_fold_lane_kernel(const typename P::S *__restrict__ in, typename P::SO *__res
         S v[VEC];
         nxc_load_vec<S, VEC>(p + off, v);
 #pragma unroll
-        for (int j = 0; j < VEC; j++) acc[j] = P::combine(acc[j], P::make(v[j], r));
+        for (int j = 0; j < VEC; j++) P::step(acc[j], v[j], r);
       }
     }
   }

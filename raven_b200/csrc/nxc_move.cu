@@ -108,7 +108,6 @@ __device__ __forceinline__ bool idx_offsets(const IdxArgs &a, int64_t it, const 
   int64_t o_idx = 0;
   o_iter = 0;
   o_tgt = 0;
-  int64_t axis_coord_off = 0;
   if (a.small) {
     uint32_t r = (uint32_t)it;
     for (int d = a.ndim - 1; d >= 0; d--) {
@@ -129,7 +128,6 @@ __device__ __forceinline__ bool idx_offsets(const IdxArgs &a, int64_t it, const 
       if (d != a.axis) o_tgt += c * a.s_tgt[d];
     }
   }
-  (void)axis_coord_off;
   int64_t ix = idx[o_idx];
   if (ix < 0) ix += a.axis_len;
   if (ix < 0 || ix >= a.axis_len) return false;

@@ -27,22 +27,10 @@ __device__ __forceinline__ double m_tan(double x) { return tan(x); }
 __device__ __forceinline__ float m_sinh(float x) { return (float)sinh((double)x); }
 __device__ __forceinline__ double m_sinh(double x) { return sinh(x); }
 __device__ __forceinline__ float m_tanh(float x) { return (float)tanh((double)x); }
-// f64 tanh: CUDA's tanh measured 3 ulp from glibc; the fdlibm formulation over expm1
-// (the one glibc uses) stays inside 2.
-__device__ __forceinline__ double m_tanh(double x) {
-  const double ax = fabs(x);
-  if (!(ax < 22.0)) return (x != x) ? x : copysign(1.0, x);
-  if (ax < 0x1p-55) return x;
-  double z;
-  if (ax >= 1.0) {
-    const double t = expm1(2.0 * ax);
-    z = 1.0 - 2.0 / (t + 2.0);
-  } else {
-    const double t = expm1(-2.0 * ax);
-    z = -t / (t + 2.0);
-  }
-  return copysign(z, x);
-}
+// f64 tanh is CUDA's: measured 3 ulp from glibc at worst over 2^20 samples (every other
+// f64 op stays within 2); an fdlibm-style expm1 formulation gave identical bits, so the
+// residual is libdevice's expm1/exp itself. Stated as the one 3-ulp exception in DESIGN.md.
+__device__ __forceinline__ double m_tanh(double x) { return tanh(x); }
 NXC_M1(trunc, truncf, trunc) NXC_M1(ceil, ceilf, ceil) NXC_M1(floor, floorf, floor)
 NXC_M1(round, roundf, round) NXC_M1(erf, erff, erf) NXC_M1(fabs, fabsf, fabs)
 #undef NXC_M1
@@ -66,8 +54,45 @@ template <> struct ZR<cf64> { typedef double R; };
 template <class Z> __device__ __forceinline__ Z zmk(typename ZR<Z>::R re, typename ZR<Z>::R im) { Z z; z.re = re; z.im = im; return z; }
 template <class Z> __device__ __forceinline__ Z zadd(Z a, Z b) { return zmk<Z>(a.re + b.re, a.im + b.im); }
 template <class Z> __device__ __forceinline__ Z zsub(Z a, Z b) { return zmk<Z>(a.re - b.re, a.im - b.im); }
-template <class Z> __device__ __forceinline__ Z zmul(Z a, Z b) {
-  return zmk<Z>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+__device__ __forceinline__ bool m_isinf(float x) { return isinf(x); }
+__device__ __forceinline__ bool m_isinf(double x) { return isinf(x); }
+// (a+bi)(c+di) with the C99 Annex G.5.1 recovery the reference's `*` on _Complex performs
+// (an infinite operand must give an infinite, not NaN, product). The slow branch runs only
+// when both parts came out NaN.
+template <class Z> __device__ __forceinline__ Z zmul(Z p, Z q) {
+  typedef typename ZR<Z>::R R;
+  R a = p.re, b = p.im, c = q.re, d = q.im;
+  R x = a * c - b * d, y = a * d + b * c;
+  if (x != x && y != y) {
+    bool recalc = false;
+    if (m_isinf(a) || m_isinf(b)) {
+      a = m_copysign(m_isinf(a) ? (R)1 : (R)0, a);
+      b = m_copysign(m_isinf(b) ? (R)1 : (R)0, b);
+      if (c != c) c = m_copysign((R)0, c);
+      if (d != d) d = m_copysign((R)0, d);
+      recalc = true;
+    }
+    if (m_isinf(c) || m_isinf(d)) {
+      c = m_copysign(m_isinf(c) ? (R)1 : (R)0, c);
+      d = m_copysign(m_isinf(d) ? (R)1 : (R)0, d);
+      if (a != a) a = m_copysign((R)0, a);
+      if (b != b) b = m_copysign((R)0, b);
+      recalc = true;
+    }
+    if (!recalc && (m_isinf(a * c) || m_isinf(b * d) || m_isinf(a * d) || m_isinf(b * c))) {
+      if (a != a) a = m_copysign((R)0, a);
+      if (b != b) b = m_copysign((R)0, b);
+      if (c != c) c = m_copysign((R)0, c);
+      if (d != d) d = m_copysign((R)0, d);
+      recalc = true;
+    }
+    if (recalc) {
+      const R inf = (R)INFINITY;
+      x = inf * (a * c - b * d);
+      y = inf * (a * d + b * c);
+    }
+  }
+  return zmk<Z>(x, y);
 }
 // Smith's division: the scaled form C compilers use for `a / b` on _Complex.
 template <class Z> __device__ __forceinline__ Z zdiv(Z a, Z b) {

@@ -80,7 +80,9 @@ class NcclComm:
 
 def slab_bounds(extent: int, rank: int, world: int):
     """Equal leading-axis slabs; the last ranks take one element less when the extent
-    does not divide (first `extent % world` ranks get the extra one)."""
+    does not divide (first `extent % world` ranks get the extra one). The allgather
+    paths (kept-axis reductions, argreduce along another axis, gathered matmul) need
+    equal slabs -- NCCL's allgather moves the same byte count from every rank."""
     base, extra = divmod(extent, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
@@ -136,7 +138,7 @@ def allreduce_mean_(tensors, comm, backend=B):
     out = []
     for t in tensors:
         t = backend.contiguous(t)
-        comm.allreduce(t, "sum")
+        t = comm.allreduce(t, "sum")
         inv = backend.expand(backend.full(t.context, t.dtype, [], 1.0 / comm.world), t.shape) if len(t.shape) \
             else backend.full(t.context, t.dtype, [], 1.0 / comm.world)
         out.append(backend.mul(t, inv))

@@ -228,7 +228,9 @@ def test_large_unary_ulp(ctx, oracle, op, dtype):
     hv = H.HostView(H.to_storage(dtype, x), dtype, [n])
     want = oracle.unary(op, hv).numpy()
     got = H.download(getattr(B, op)(H.upload(ctx, hv)))
-    H.assert_same(dtype, got, want, ulp=(0 if op in ("sqrt", "recip") else 2), what=f"{op}/{dtype}")
+    # the one stated exception to the 2-ulp bound: f64 tanh (libdevice), 3 ulp
+    ulp = 0 if op in ("sqrt", "recip") else (3 if (op, dtype) == ("tanh", "f64") else 2)
+    H.assert_same(dtype, got, want, ulp=ulp, what=f"{op}/{dtype}")
 
 
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
