@@ -1,0 +1,234 @@
+/* nx_cuda_stubs.c -- OCaml externals over libnxcuda (include/nxcuda.h).
+ *
+ * One stub per external in nx_backend.ml. Each extracts slots 0-4 of the tensor
+ * record into an nxc_tensor (the same slots, in the same order, that the reference
+ * reads: packages/nx/lib/backend_c/nx_c.h:47-61, 420-434), calls one nxc_* entry
+ * point (an asynchronous launch on the context stream) and maps a non-NULL status to
+ * Invalid_argument / Failure "<op>: <status>" exactly as the reference's funnel does
+ * (nx_c_engine.c:42-52, 1345-1351). UNVERIFIED: never compiled here (no OCaml).
+ */
+#include <stdio.h>
+#include <string.h>
+
+#include <caml/alloc.h>
+#include <caml/bigarray.h>
+#include <caml/custom.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+#include <caml/threads.h>
+
+#include "nxcuda.h"
+
+typedef struct { void *ptr; size_t bytes; nxc_ctx *ctx; } devbuf;
+#define Devbuf_val(v) ((devbuf *)Data_custom_val(v))
+#define Ctx_val(v) (*(nxc_ctx **)Data_custom_val(v))
+
+static void devbuf_finalize(value v) {
+  devbuf *b = Devbuf_val(v);
+  if (b->ptr) nxc_free(b->ctx, b->ptr); /* cudaFreeAsync: ordered after in-flight kernels */
+}
+static struct custom_operations devbuf_ops = {"nx_cuda.devbuf", devbuf_finalize, custom_compare_default,
+    custom_hash_default, custom_serialize_default, custom_deserialize_default, custom_compare_ext_default,
+    custom_fixed_length_default};
+static struct custom_operations ctx_ops = {"nx_cuda.ctx", custom_finalize_default, custom_compare_default,
+    custom_hash_default, custom_serialize_default, custom_deserialize_default, custom_compare_ext_default,
+    custom_fixed_length_default};
+
+static void raise_status(const char *op, nxc_ctx *ctx, nxc_status s) {
+  char buf[640];
+  if (strcmp(s, "CUDA error") == 0 || strcmp(s, "NCCL error") == 0)
+    snprintf(buf, sizeof buf, "%s: %s [%s]", op, s, nxc_last_error(ctx));
+  else
+    snprintf(buf, sizeof buf, "%s: %s", op, s);
+  if (nxc_status_is_invalid_argument(s)) caml_invalid_argument(buf);
+  caml_failwith(buf);
+}
+
+/* record slots: 0 buffer, 1 shape, 2 strides, 3 offset, 4 tag, 5 context */
+static void tensor_of_value(value v, nxc_tensor *t) {
+  value sh = Field(v, 1), st = Field(v, 2);
+  int nd = (int)Wosize_val(sh);
+  if (nd > NXC_MAX_NDIM) caml_failwith("ndim exceeds NX_C_MAX_NDIM");
+  t->data = Devbuf_val(Field(v, 0))->ptr;
+  t->dtype = Int_val(Field(v, 4));
+  t->ndim = nd;
+  for (int i = 0; i < nd; i++) { t->shape[i] = Long_val(Field(sh, i)); t->strides[i] = Long_val(Field(st, i)); }
+  t->offset = Long_val(Field(v, 3));
+}
+#define CTX_OF(v) Ctx_val(Field((v), 5))
+
+CAMLprim value nx_cuda_ctx_create(value unit) {
+  CAMLparam1(unit);
+  CAMLlocal1(v);
+  nxc_ctx *ctx = NULL;
+  nxc_status s = nxc_ctx_create(&ctx);
+  if (s) raise_status("create_context", NULL, s);
+  v = caml_alloc_custom(&ctx_ops, sizeof(nxc_ctx *), 0, 1);
+  Ctx_val(v) = ctx;
+  CAMLreturn(v);
+}
+CAMLprim value nx_cuda_alloc(value vctx, value vbytes) {
+  CAMLparam2(vctx, vbytes);
+  CAMLlocal1(v);
+  size_t n = (size_t)Long_val(vbytes);
+  v = caml_alloc_custom_mem(&devbuf_ops, sizeof(devbuf), n); /* the GC sees device pressure */
+  devbuf *b = Devbuf_val(v);
+  b->ptr = NULL; b->bytes = n; b->ctx = Ctx_val(vctx);
+  nxc_status s = nxc_alloc(b->ctx, n, &b->ptr);
+  if (s) raise_status("buffer", b->ctx, s);
+  CAMLreturn(v);
+}
+CAMLprim value nx_cuda_of_host(value vctx, value vbuf) {
+  CAMLparam2(vctx, vbuf);
+  CAMLlocal1(v);
+  struct caml_ba_array *ba = Caml_ba_array_val(vbuf);
+  size_t n = caml_ba_byte_size(ba);
+  v = nx_cuda_alloc(vctx, Val_long(n ? n : 16));
+  nxc_ctx *ctx = Ctx_val(vctx);
+  nxc_status s = nxc_h2d(ctx, Devbuf_val(v)->ptr, ba->data, n);
+  if (!s) { caml_enter_blocking_section(); s = nxc_sync(ctx); caml_leave_blocking_section(); }
+  if (s) raise_status("from_host", ctx, s);
+  CAMLreturn(v);
+}
+CAMLprim value nx_cuda_to_host(value vctx, value vdev, value vbuf) {
+  CAMLparam3(vctx, vdev, vbuf);
+  struct caml_ba_array *ba = Caml_ba_array_val(vbuf);
+  nxc_ctx *ctx = Ctx_val(vctx);
+  void *src = Devbuf_val(vdev)->ptr, *dst = ba->data;
+  size_t n = caml_ba_byte_size(ba);
+  caml_enter_blocking_section(); /* the only blocking call on the path */
+  nxc_status s = nxc_d2h(ctx, dst, src, n);
+  caml_leave_blocking_section();
+  if (s) raise_status("to_host", ctx, s);
+  CAMLreturn(Val_unit);
+}
+
+static const char *UN[] = {"neg","recip","abs","sign","sqrt","exp","log","sin","cos","tan","asin","acos","atan",
+                           "sinh","cosh","tanh","trunc","ceil","floor","round","erf"};
+static const char *BIN[] = {"add","sub","mul","idiv","fdiv","mod","max","min","pow","atan2","xor","or","and","shl","shr"};
+static const char *CMP[] = {"cmpeq","cmpne","cmplt","cmple"};
+static const char *RED[] = {"reduce_sum","reduce_prod","reduce_max","reduce_min"};
+static const char *SCAN[] = {"cumsum","cumprod","cummax","cummin"};
+
+CAMLprim value nx_cuda_map1(value vop, value vout, value va) {
+  CAMLparam3(vop, vout, va);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(va, &a);
+  nxc_status s = nxc_map1(CTX_OF(vout), Int_val(vop), &o, &a);
+  if (s) raise_status(UN[Int_val(vop)], CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_map2(value vop, value vout, value va, value vb) {
+  CAMLparam4(vop, vout, va, vb);
+  nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
+  nxc_status s = nxc_map2(CTX_OF(vout), Int_val(vop), &o, &a, &b);
+  if (s) raise_status(BIN[Int_val(vop)], CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_cmp(value vop, value vout, value va, value vb) {
+  CAMLparam4(vop, vout, va, vb);
+  nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
+  nxc_status s = nxc_cmp(CTX_OF(vout), Int_val(vop), &o, &a, &b);
+  if (s) raise_status(CMP[Int_val(vop)], CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_where(value vout, value vc, value va, value vb) {
+  CAMLparam4(vout, vc, va, vb);
+  nxc_tensor o, c, a, b;
+  tensor_of_value(vout, &o); tensor_of_value(vc, &c); tensor_of_value(va, &a); tensor_of_value(vb, &b);
+  nxc_status s = nxc_where(CTX_OF(vout), &o, &c, &a, &b);
+  if (s) raise_status("where", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+#define STUB2(name, opname, call)                                             \
+  CAMLprim value nx_cuda_##name(value vout, value va) {                       \
+    CAMLparam2(vout, va);                                                     \
+    nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(va, &a);      \
+    nxc_status s = call(CTX_OF(vout), &o, &a);                                \
+    if (s) raise_status(opname, CTX_OF(vout), s);                             \
+    CAMLreturn(Val_unit);                                                     \
+  }
+STUB2(cast, "cast", nxc_cast)
+STUB2(copy, "copy", nxc_copy)
+
+CAMLprim value nx_cuda_fill(value vout, value vone) {
+  CAMLparam2(vout, vone);
+  nxc_tensor o; tensor_of_value(vout, &o);
+  nxc_status s = nxc_fill(CTX_OF(vout), &o, Caml_ba_array_val(vone)->data);
+  if (s) raise_status("full", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_reduce(value vop, value vout, value vin, value vaxes) {
+  CAMLparam4(vop, vout, vin, vaxes);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int n = (int)Wosize_val(vaxes), axes[NXC_MAX_NDIM];
+  if (n > NXC_MAX_NDIM) caml_failwith("ndim exceeds NX_C_MAX_NDIM");
+  for (int i = 0; i < n; i++) axes[i] = Int_val(Field(vaxes, i));
+  nxc_status s = nxc_reduce(CTX_OF(vout), Int_val(vop), &o, &a, axes, n);
+  if (s) raise_status(RED[Int_val(vop)], CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_argreduce(value vmax, value vout, value vin, value vaxis) {
+  CAMLparam4(vmax, vout, vin, vaxis);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  nxc_status s = nxc_argreduce(CTX_OF(vout), Bool_val(vmax), &o, &a, Int_val(vaxis));
+  if (s) raise_status(Bool_val(vmax) ? "argmax" : "argmin", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_scan(value vop, value vout, value vin, value vaxis) {
+  CAMLparam4(vop, vout, vin, vaxis);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  nxc_status s = nxc_scan(CTX_OF(vout), Int_val(vop), &o, &a, Int_val(vaxis));
+  if (s) raise_status(SCAN[Int_val(vop)], CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_matmul(value vout, value va, value vb) {
+  CAMLparam3(vout, va, vb);
+  nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
+  nxc_status s = nxc_matmul(CTX_OF(vout), &o, &a, &b);
+  if (s) raise_status("matmul", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_pad(value vout, value vin, value vone, value vbefore) {
+  CAMLparam4(vout, vin, vone, vbefore);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int64_t before[NXC_MAX_NDIM];
+  if ((int)Wosize_val(vbefore) != o.ndim) caml_invalid_argument("pad: shape mismatch");
+  for (int i = 0; i < o.ndim; i++) before[i] = Long_val(Field(vbefore, i));
+  nxc_status s = nxc_pad(CTX_OF(vout), &o, &a, Caml_ba_array_val(vone)->data, before);
+  if (s) raise_status("pad", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_cat(value vout, value vins, value vaxis) {
+  CAMLparam3(vout, vins, vaxis);
+  int n = (int)Wosize_val(vins);
+  nxc_tensor o; tensor_of_value(vout, &o);
+  nxc_tensor *ts = (nxc_tensor *)caml_stat_alloc(sizeof(nxc_tensor) * (n ? n : 1));
+  const nxc_tensor **ps = (const nxc_tensor **)caml_stat_alloc(sizeof(void *) * (n ? n : 1));
+  for (int i = 0; i < n; i++) { tensor_of_value(Field(vins, i), &ts[i]); ps[i] = &ts[i]; }
+  nxc_status s = nxc_cat(CTX_OF(vout), &o, ps, n, Int_val(vaxis));
+  caml_stat_free(ts); caml_stat_free(ps);
+  if (s) raise_status("cat", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_gather(value vout, value vdata, value vidx, value vaxis) {
+  CAMLparam4(vout, vdata, vidx, vaxis);
+  nxc_tensor o, d, i; tensor_of_value(vout, &o); tensor_of_value(vdata, &d); tensor_of_value(vidx, &i);
+  nxc_status s = nxc_gather(CTX_OF(vout), &o, &d, &i, Int_val(vaxis));
+  if (s) raise_status("gather", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_scatter(value vout, value vidx, value vupd, value vaxis, value vmode) {
+  CAMLparam5(vout, vidx, vupd, vaxis, vmode);
+  nxc_tensor o, i, u; tensor_of_value(vout, &o); tensor_of_value(vidx, &i); tensor_of_value(vupd, &u);
+  nxc_status s = nxc_scatter(CTX_OF(vout), &o, &i, &u, Int_val(vaxis), Int_val(vmode));
+  if (s) raise_status("scatter", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_threefry(value vout, value vkey, value vctr) {
+  CAMLparam3(vout, vkey, vctr);
+  nxc_tensor o, k, c; tensor_of_value(vout, &o); tensor_of_value(vkey, &k); tensor_of_value(vctr, &c);
+  nxc_status s = nxc_threefry(CTX_OF(vout), &o, &k, &c);
+  if (s) raise_status("threefry", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
