@@ -170,9 +170,9 @@ def test_accumulator_witnesses(ctx):
     from raven_b200 import dtype as D
     ones = B.full(ctx, D.float32, [1 << 25], 1.0)
     assert float(H.download(B.reduce(ones, "sum", [0]))) == float(1 << 25)
-    h = B.full(ctx, D.float16, [4096], np.float16(1.0).view(np.uint16))
+    h = B.full(ctx, D.float16, [4096], 1.0)
     assert H.download(B.reduce(h, "sum", [0])).view(np.float16) == np.float16(4096)
-    b = B.full(ctx, D.bfloat16, [512], 0x3F80)
+    b = B.full(ctx, D.bfloat16, [512], 1.0)
     assert int(H.download(B.reduce(b, "sum", [0]))) == 0x4400  # 512.0 in bf16
     # bool: max = any, min = all (backend_contract.ml:2425-2432)
     m = np.ones(1000, dtype=np.uint8)
