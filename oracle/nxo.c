@@ -513,10 +513,11 @@ nxo_status nxo_where(const nxo_tensor *out, const nxo_tensor *c, const nxo_tenso
 }
 
 /* ==== copy (nx_c_move.c:61-84) ========================================================== */
+static nxo_status copy_packed(const nxo_tensor *out, const nxo_tensor *in);
 nxo_status nxo_copy(const nxo_tensor *out, const nxo_tensor *a) {
   nxo_status s;
   if ((s = chk(out)) || (s = chk(a))) return s;
-  if (DT_CAT[out->dtype] & CAT_PACKED) return E_PACKED;
+  if (DT_CAT[out->dtype] & CAT_PACKED) return copy_packed(out, a);
   if ((s = out_aliased(out))) return s;
   int es = DT_SIZE[out->dtype];
   odo o;
@@ -589,10 +590,11 @@ static val cast_apply(int src, int dst, val v) {
   }
   return r;
 }
+static nxo_status cast_packed(const nxo_tensor *out, const nxo_tensor *in);
 nxo_status nxo_cast(const nxo_tensor *out, const nxo_tensor *a) {
   nxo_status s;
   if ((s = chk(out)) || (s = chk(a))) return s;
-  if ((DT_CAT[out->dtype] | DT_CAT[a->dtype]) & CAT_PACKED) return E_PACKED;
+  if ((DT_CAT[out->dtype] | DT_CAT[a->dtype]) & CAT_PACKED) return cast_packed(out, a);
   if ((s = out_aliased(out))) return s;
   odo o;
   odo_init(&o, out->ndim, out->shape);
@@ -600,6 +602,78 @@ nxo_status nxo_cast(const nxo_tensor *out, const nxo_tensor *a) {
   odo_add(&o, a, NULL);
   for (int64_t i = 0; i < o.total; i++, odo_next(&o))
     st(out->dtype, o.ptr[0], cast_apply(a->dtype, out->dtype, ld(a->dtype, o.ptr[1])));
+  return NULL;
+}
+
+
+/* ==== packed int4 / uint4 (storage-only): nx_c_map.c:1046-1177, nx_c_move.c:151-189 ===== */
+static int packed_dense(const nxo_tensor *a) {
+  int64_t expect = 1;
+  for (int i = a->ndim - 1; i >= 0; i--) {
+    if (a->shape[i] == 1) continue;
+    if (a->strides[i] != expect) return 0;
+    expect *= a->shape[i];
+  }
+  return 1;
+}
+static int get_nib(const uint8_t *b, int64_t i, int sgn) {
+  uint8_t by = b[i >> 1];
+  if (sgn) return (i & 1) ? ((int8_t)by >> 4) : ((int8_t)((by & 0x0F) << 4) >> 4);
+  return (i & 1) ? (by >> 4) : (by & 0x0F);
+}
+static void put_nib(uint8_t *b, int64_t i, unsigned nib) {
+  uint8_t *bp = &b[i >> 1];
+  *bp = (i & 1) ? (uint8_t)((*bp & 0x0F) | ((nib & 0xF) << 4)) : (uint8_t)((*bp & 0xF0) | (nib & 0xF));
+}
+static int f2i4(double v, int sgn) {
+  if (isnan(v)) return 0;
+  if (sgn) { if (v <= -8.0) return -8; if (v >= 7.0) return 7; }
+  else { if (v <= 0.0) return 0; if (v >= 15.0) return 15; }
+  return (int)v;
+}
+static nxo_status cast_packed(const nxo_tensor *out, const nxo_tensor *in) {
+  if (!packed_dense(out) || !packed_dense(in)) return E_PACKED;
+  int64_t n = 1;
+  for (int i = 0; i < out->ndim; i++) n *= out->shape[i];
+  int src = in->dtype, dst = out->dtype;
+  int sp = (DT_CAT[src] & CAT_PACKED) != 0, dp = (DT_CAT[dst] & CAT_PACKED) != 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (sp && dp) {
+      put_nib((uint8_t *)out->data, out->offset + i, (unsigned)get_nib((const uint8_t *)in->data, in->offset + i, 0));
+    } else if (dp) {
+      val v = ld(src, (const char *)in->data + (in->offset + i) * DT_SIZE[src]);
+      int sgn = dst == I4, nib;
+      switch (DT_KIND[src]) {
+        case K_F32: nib = f2i4((double)v.f, sgn); break;
+        case K_F64: nib = f2i4(v.d, sgn); break;
+        case K_C32: nib = f2i4((double)crealf(v.c32), sgn); break;
+        case K_C64: nib = f2i4(creal(v.c64), sgn); break;
+        case K_U64: nib = (int)v.u; break;
+        case K_BOOL: nib = v.b; break;
+        default: nib = (int)v.i; break;
+      }
+      put_nib((uint8_t *)out->data, out->offset + i, (unsigned)nib);
+    } else {
+      int nv = get_nib((const uint8_t *)in->data, in->offset + i, src == I4);
+      val v;
+      memset(&v, 0, sizeof v);
+      v.i = nv; /* the nibble as a small signed / unsigned integer, then the cast policy */
+      st(dst, (char *)out->data + (out->offset + i) * DT_SIZE[dst], cast_apply(src == I4 ? I8 : U8, dst, v));
+    }
+  }
+  return NULL;
+}
+static nxo_status copy_packed(const nxo_tensor *out, const nxo_tensor *in) {
+  int64_t n = 1, m = 1;
+  for (int i = 0; i < out->ndim; i++) n *= out->shape[i];
+  for (int i = 0; i < in->ndim; i++) m *= in->shape[i];
+  if (n != m || out->offset != 0 || in->offset != 0 || !packed_dense(out) || !packed_dense(in)) return E_PACKED;
+  memcpy(out->data, in->data, (size_t)(n / 2));
+  if (n & 1) { /* odd tail: merge only the low nibble, the neighbour's high nibble survives */
+    uint8_t *d = (uint8_t *)out->data + n / 2;
+    const uint8_t *sp = (const uint8_t *)in->data + n / 2;
+    *d = (uint8_t)((*d & 0xF0) | (*sp & 0x0F));
+  }
   return NULL;
 }
 

@@ -126,9 +126,17 @@ template <int OP, int DT> struct RedP {
       else return a * b;
     } else if constexpr (cls == NXC_CLS_FLOAT) {
       // NaN sticks (reference: nx_c_fold.c:80-89)
-      if (a != a) return a;
-      if (b != b) return b;
-      return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
+      if constexpr (sizeof(A) == 4) {
+        // one instruction: max.NaN / min.NaN return NaN if either input is NaN
+        float r;
+        if (OP == NXC_RMAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        return r;
+      } else {
+        if (a != a) return a;
+        if (b != b) return b;
+        return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
+      }
     } else {
       return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
     }

@@ -70,6 +70,7 @@ struct NxcRowArgs {
   int64_t chunk;      // reduced elements per split (multiple of the vector width)
   int S;              // splits
   int tpr_log2;       // threads per output row (log2), TPR * RPB == NXC_FOLD_THREADS
+  int G;              // rows folded concurrently per thread group (1 or 4)
   int small;          // all linear indices < 2^31
 };
 
@@ -120,6 +121,55 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
   const int split = (int)((int64_t)blockIdx.x - rowblock * a.S);
   const int64_t o = rowblock * RPB + row_in_block;
   const bool live = o < a.O;
+  // Short rows (fewer than 256 work items per output, no split): one thread group folds G
+  // adjacent-by-group rows at once so G independent vector loads are in flight per thread.
+  if (a.G > 1) {
+    constexpr int G = 4;
+    A accg[G];
+    int64_t ib[G], ob[G];
+    bool lv[G];
+    const int64_t o_base = rowblock * ((int64_t)RPB * G) + row_in_block;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      accg[g] = P::identity();
+      const int64_t og = o_base + (int64_t)g * RPB;
+      lv[g] = og < a.O;
+      ib[g] = 0; ob[g] = 0;
+      if (lv[g]) nxc_dims_offset(a.kept, og, a.small, ib[g], ob[g]);
+    }
+    const int64_t stepg = (int64_t)TPR * VEC;
+    for (int64_t r = (int64_t)tr * VEC; r < a.R; r += stepg) {
+      S v[G][VEC];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        if (lv[g]) {
+          if (VEC > 1) nxc_load_vec<S, VEC>(in + ib[g] + r, v[g]);
+          else v[g][0] = in[ib[g] + r * a.s_inner];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++)
+        if (lv[g]) {
+#pragma unroll
+          for (int j = 0; j < VEC; j++) P::step(accg[g], v[g][j], r + j);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      A t = accg[g];
+      if (TPR <= 32) {
+        for (int m = TPR >> 1; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
+      } else {
+        for (int m = 16; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
+        __syncthreads();
+        sm[threadIdx.x] = t;
+        __syncthreads();
+        if (tr == 0) for (int w = 32; w < TPR; w += 32) t = P::combine(t, sm[threadIdx.x + w]);
+      }
+      if (lv[g] && tr == 0) out[ob[g]] = P::finish(t);
+    }
+    return;
+  }
   A acc[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) acc[i] = P::identity();
@@ -444,7 +494,8 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   if (tl > 8) tl = 8;
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
-  const int64_t rowblocks = (p.O + RPB - 1) / RPB;
+  a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * 4 * ctx->sm_count) ? 4 : 1;
+  const int64_t rowblocks = (p.O + (int64_t)RPB * a.G - 1) / ((int64_t)RPB * a.G);
   int64_t S_ = 1;
   if (rowblocks < target_blocks && tl == 8) {
     S_ = (target_blocks + rowblocks - 1) / rowblocks;

@@ -6,6 +6,9 @@
 
 #include "nxc_map_groups.cuh"
 
+nxc_status nxc_cast_packed(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in);
+nxc_status nxc_copy_packed(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in);
+
 static const int CLS_NUM = NXC_CLS_SINT | NXC_CLS_UINT | NXC_CLS_FLOAT | NXC_CLS_COMPLEX;
 static const int CLS_FC = NXC_CLS_FLOAT | NXC_CLS_COMPLEX;
 static const int CLS_INTF = NXC_CLS_SINT | NXC_CLS_UINT | NXC_CLS_FLOAT;
@@ -139,7 +142,7 @@ extern "C" nxc_status nxc_cast(nxc_ctx *ctx, const nxc_tensor *out, const nxc_te
   nxc_status s;
   for (int k = 0; k < 2; k++)
     if ((s = nxc_check_tensor(ops[k]))) return fail(ctx, s);
-  if (nxc_is_packed(out->dtype) || nxc_is_packed(a->dtype)) return fail(ctx, NXC_ERR_PACKED);
+  if (nxc_is_packed(out->dtype) || nxc_is_packed(a->dtype)) return fail(ctx, nxc_cast_packed(ctx, out, a));
   if ((s = same_shape(ops, 2))) return fail(ctx, s);
   const int64_t es[2] = {nxc_elem_size(out->dtype), nxc_elem_size(a->dtype)};
   NxcMapPlan p;
@@ -159,6 +162,9 @@ nxc_status nxc_cast_group(nxc_ctx *ctx, int src, int dst, const NxcMapPlan &p) {
 
 extern "C" nxc_status nxc_copy(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a) {
   const nxc_tensor *ops[2] = {out, a};
+  if (nxc_valid_dtype(out->dtype) && nxc_is_packed(out->dtype) && a->dtype == out->dtype && out->ndim <= NXC_MAX_NDIM &&
+      a->ndim <= NXC_MAX_NDIM)
+    return fail(ctx, nxc_copy_packed(ctx, out, a));
   nxc_status s = check_ops(ops, 2);
   if (s) return fail(ctx, s);
   if (a->dtype != out->dtype) return fail(ctx, NXC_ERR_UNSUPPORTED_DTYPE);

@@ -28,6 +28,7 @@ template <class T> struct KWhere {
   __device__ __forceinline__ static S0 run(S1 c, S2 a, S3 b, const P &) { return c ? a : b; }
 };
 template <class T> struct KCopy {
+  static constexpr bool TILED = sizeof(T) <= 8;  // contiguous(transpose x): shared-memory tile transpose
   static constexpr int NIN = 1;
   typedef T S0; typedef T S1; typedef T S2; typedef T S3;
   typedef NxcNoP P;

@@ -331,6 +331,9 @@ template <int OP, int DT> struct KUn {
 };
 template <int OP, int DT> struct KBin {
   typedef DT_<DT> D;
+  // a transposed operand goes through the shared-memory tiled kernel for the hot arithmetic ops
+  static constexpr bool TILED = (OP == NXC_ADD || OP == NXC_SUB || OP == NXC_MUL || OP == NXC_FDIV ||
+                                 OP == NXC_MAX || OP == NXC_MIN) && sizeof(typename DT_<DT>::S) <= 8;
   typedef Bin<OP, typename D::C, D::cls, 8 * (int)sizeof(typename D::S)> O;
   static constexpr int NIN = 2;
   typedef typename D::S S0; typedef typename D::S S1; typedef typename D::S S2; typedef typename D::S S3;

@@ -133,3 +133,51 @@ def test_scan(ctx, oracle, op, dt):
                 H.assert_close(dt, got, want, rel=1e-5, abs_=1e-5, what=f"cum{op}/{dt}")
             else:
                 H.assert_same(dt, got, want, ulp=0, what=f"cum{op}/{dt}/{hv.shape}/{axis}")
+
+
+def _dev_packed(ctx, hv):
+    """Upload a packed HostView: storage bytes verbatim, nibble shape/offset on the handle."""
+    from raven_b200 import dtype as D
+    base = B.from_host(ctx, hv.storage, D.of(hv.dtype))
+    return B.Tensor(base.buffer, hv.shape, hv.strides, hv.offset, base.dtype, ctx)
+
+
+@pytest.mark.parametrize("pk", ["i4", "u4"])
+def test_packed_int4(ctx, oracle, pk):
+    """int4 / uint4 casts for every compute dtype at odd nibble offsets, packed->packed, and the
+    odd-length prefix assign that must keep the neighbour nibble (backend_contract.ml:1402-1603)."""
+    from raven_b200 import dtype as D
+    from tests.test_gpu_map import _cast_inputs
+    rng = np.random.default_rng(3)
+    for dt in list(H.FLOATS) + list(H.INTS) + list(H.COMPLEX) + ["bool"]:
+        data = _cast_inputs(dt)
+        src = H.HostView(data.copy(), dt, [data.size])
+        # compute -> packed into a pre-filled buffer at nibble offset 1: neighbours must survive
+        want = H.HostView(np.full((data.size + 3) // 2 + 1, 0xA5, np.uint8), pk, [data.size], None, 1)
+        oracle.assign  # noqa: B018  (oracle module present)
+        import ctypes
+        if oracle.__name__.endswith("ref"):
+            oracle.call("cast", want, src)
+        else:
+            oracle._chk("cast", oracle.lib().nxo_cast(ctypes.byref(oracle._d(want)), ctypes.byref(oracle._d(src))))
+        got_hv = H.HostView(np.full((data.size + 3) // 2 + 1, 0xA5, np.uint8), pk, [data.size], None, 1)
+        out_t = _dev_packed(ctx, got_hv)
+        do, ds = out_t._desc(), H.upload(ctx, src)._desc()
+        st = ctx._lib.nxc_cast(ctx.ptr, ctypes.byref(do), ctypes.byref(ds))
+        assert not st, st
+        assert np.array_equal(B.to_host(out_t), want.storage), f"cast {dt}->{pk}"
+        # packed -> compute from nibble offset 3
+        packed = H.HostView(rng.integers(0, 256, 9).astype(np.uint8), pk, [15], None, 3)
+        w = oracle.cast(packed, dt).numpy()
+        g = H.download(B.cast(_dev_packed(ctx, packed), D.of(dt)))
+        assert np.array_equal(H.raw(g), H.raw(w)), f"cast {pk}->{dt}"
+    # odd-length prefix assign keeps the neighbour's high nibble
+    base = _dev_packed(ctx, H.HostView(np.full(4, 0xFF, np.uint8), pk, [8]))
+    prefix = B.Tensor(base.buffer, (5,), (1,), 0, base.dtype, ctx)
+    B.assign(prefix, _dev_packed(ctx, H.HostView(np.array([0x21, 0x43, 0x05], np.uint8), pk, [5])))
+    assert B.to_host(base).tolist() == [0x21, 0x43, 0xF5, 0xFF]
+    strided = B.permute(_dev_packed(ctx, H.HostView(np.zeros(8, np.uint8), pk, [4, 4])), [1, 0])
+    with pytest.raises(Failure, match="cast: packed dtype not supported for this operation"):
+        B.cast(strided, D.float32)
+    with pytest.raises(Failure, match="add: packed dtype not supported for this operation"):
+        B.add(base, base)

@@ -209,3 +209,38 @@ def test_move_and_random_match_reference():
     _same("i32", r, o, "threefry")
     r, o = _both(lambda m: m.threefry(H.HostView(np.zeros(6, np.int32), "i32", [2, 3]), H.HostView(np.zeros(6, np.int32), "i32", [2, 3])))
     assert isinstance(r, tuple) and r == o and r[1] == "Invalid_argument", (r, o)
+
+
+def test_packed_int4_matches_reference():
+    """int4 / uint4: cast both ways for every compute dtype, nibble offsets, packed->packed,
+    and the odd-length prefix assign that must keep the neighbour nibble
+    (backend_contract.ml:1402-1513, 1517-1603)."""
+    rng = np.random.default_rng(3)
+    for pk in ("i4", "u4"):
+        for dt in ALL:
+            from tests.test_gpu_map import _cast_inputs
+            data = _cast_inputs(dt)
+            src = H.HostView(data.copy(), dt, [data.size])
+            outs = []
+            for m in (ref, nxo):
+                out = H.HostView(np.full((data.size + 3) // 2 + 1, 0xA5, np.uint8), pk, [data.size], None, 1)
+                m.call("cast", out, src) if m is ref else nxo._chk("cast", nxo.lib().nxo_cast(
+                    __import__("ctypes").byref(nxo._d(out)), __import__("ctypes").byref(nxo._d(src))))
+                outs.append(out.storage.copy())
+            assert np.array_equal(outs[0], outs[1]), f"cast {dt}->{pk}"
+            packed = H.HostView(rng.integers(0, 256, 9).astype(np.uint8), pk, [15], None, 3)
+            r, o = _both(lambda m: m.cast(packed, dt))
+            _same(dt, r, o, f"cast {pk}->{dt}")
+        a = H.HostView(rng.integers(0, 256, 8).astype(np.uint8), pk, [13], None, 2)
+        r, o = _both(lambda m: m.cast(a, "u4" if pk == "i4" else "i4"))
+        assert np.array_equal(r.storage, o.storage)
+        res = []
+        for m in (ref, nxo):
+            base = H.HostView(np.full(4, 0xFF, np.uint8), pk, [8])
+            prefix = H.HostView(base.storage, pk, [5])
+            m.assign(prefix, H.HostView(np.array([0x21, 0x43, 0x05], np.uint8), pk, [5]))
+            res.append(base.storage.copy())
+        assert np.array_equal(res[0], res[1]) and res[0].tolist() == [0x21, 0x43, 0xF5, 0xFF]
+        strided = H.HostView(np.zeros(8, np.uint8), pk, [4, 4]).permute([1, 0])
+        r, o = _both(lambda m: m.cast(strided, "f32"))
+        assert isinstance(r, tuple) and r == o and "packed" in r[2]
