@@ -1,8 +1,7 @@
 // nxc_fold.cu -- reduce_sum / reduce_prod / reduce_max / reduce_min.
 // Replaces caml_nx_c_reduce_* (reference: nx_c_fold.c:824-831) with the funnel
 // and driver checks of nx_c_engine.c:1392-1452, 1052-1105.
-#include "nxc_ops.cuh"
-#include "nxc_fold.cuh"
+#include "nxc_fold_policy.cuh"
 #include "nxc_map_groups.cuh"
 
 // ---- the plan (shared with argreduce) -------------------------------------------------
@@ -82,68 +81,6 @@ nxc_status nxc_fold_plan(const nxc_tensor *in, const nxc_tensor *out, const int 
   return NXC_OK;
 }
 
-// ---- reduction policies ------------------------------------------------------------------
-template <class C, int CLS> struct Lim;
-template <> struct Lim<float, NXC_CLS_FLOAT> { __device__ static float lo() { return -INFINITY; } __device__ static float hi() { return INFINITY; } };
-template <> struct Lim<double, NXC_CLS_FLOAT> { __device__ static double lo() { return -INFINITY; } __device__ static double hi() { return INFINITY; } };
-template <> struct Lim<int32_t, NXC_CLS_SINT> { __device__ static int32_t lo() { return INT32_MIN; } __device__ static int32_t hi() { return INT32_MAX; } };
-template <> struct Lim<int64_t, NXC_CLS_SINT> { __device__ static int64_t lo() { return INT64_MIN; } __device__ static int64_t hi() { return INT64_MAX; } };
-template <> struct Lim<uint32_t, NXC_CLS_UINT> { __device__ static uint32_t lo() { return 0; } __device__ static uint32_t hi() { return UINT32_MAX; } };
-template <> struct Lim<uint64_t, NXC_CLS_UINT> { __device__ static uint64_t lo() { return 0; } __device__ static uint64_t hi() { return UINT64_MAX; } };
-template <> struct Lim<uint32_t, NXC_CLS_BOOL> { __device__ static uint32_t lo() { return 0; } __device__ static uint32_t hi() { return 1; } };
-
-template <int OP, int DT> struct RedP {
-  typedef DT_<DT> D;
-  typedef typename D::S S;
-  typedef typename D::S SO;
-  typedef typename D::C A;
-  static constexpr int cls = D::cls;
-  static constexpr bool ok = (OP == NXC_SUM || OP == NXC_PROD)
-                                 ? (cls != NXC_CLS_BOOL)
-                                 : (cls != NXC_CLS_COMPLEX);
-  __device__ __forceinline__ static A identity() {
-    if constexpr (cls == NXC_CLS_COMPLEX) {
-      return zmk<A>(OP == NXC_PROD ? 1 : 0, 0);
-    } else if constexpr (OP == NXC_SUM) {
-      return (A)0;
-    } else if constexpr (OP == NXC_PROD) {
-      return (A)1;
-    } else if constexpr (OP == NXC_RMAX) {
-      return Lim<A, cls>::lo();
-    } else {
-      return Lim<A, cls>::hi();
-    }
-  }
-  __device__ __forceinline__ static void step(A &acc, S s, int64_t) { acc = combine(acc, D::ld(s)); }
-  __device__ __forceinline__ static A combine(A a, A b) {
-    if constexpr (cls == NXC_CLS_COMPLEX) {
-      return OP == NXC_SUM ? zadd(a, b) : zmul(a, b);
-    } else if constexpr (OP == NXC_SUM) {
-      if constexpr (cls == NXC_CLS_SINT) return (A)((typename UT<A>::U)a + (typename UT<A>::U)b);
-      else return a + b;
-    } else if constexpr (OP == NXC_PROD) {
-      if constexpr (cls == NXC_CLS_SINT) return (A)((typename UT<A>::U)a * (typename UT<A>::U)b);
-      else return a * b;
-    } else if constexpr (cls == NXC_CLS_FLOAT) {
-      // NaN sticks (reference: nx_c_fold.c:80-89)
-      if constexpr (sizeof(A) == 4) {
-        // one instruction: max.NaN / min.NaN return NaN if either input is NaN
-        float r;
-        if (OP == NXC_RMAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-        else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-        return r;
-      } else {
-        if (a != a) return a;
-        if (b != b) return b;
-        return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
-      }
-    } else {
-      return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
-    }
-  }
-  __device__ __forceinline__ static SO finish(A a) { return D::st(a); }
-};
-
 static void identity_bytes(int op, int dt, void *buf) {
   memset(buf, 0, 16);
   if (op != NXC_PROD) return;
@@ -158,12 +95,11 @@ static void identity_bytes(int op, int dt, void *buf) {
   }
 }
 
-#define NXC_RED_CASE(OPC)                                                          \
-  case OPC: {                                                                      \
-    NXC_DISPATCH_DTYPE(dt, {                                                       \
-      st = NxcMaybeFold<RedP<OPC, DT>, RedP<OPC, DT>::ok>::go(ctx, p); \
-    })                                                                             \
-  } break;
+nxc_status nxc_reduce_sumprod(nxc_ctx *ctx, int op, int dt, const NxcFoldPlan &p) {
+  nxc_status st = NXC_ERR_UNSUPPORTED_DTYPE;
+  switch (op) { NXC_RED_CASE(NXC_SUM) NXC_RED_CASE(NXC_PROD) default: break; }
+  return st;
+}
 
 extern "C" nxc_status nxc_reduce(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *in,
                                  const int *axes, int n_axes) {
@@ -199,12 +135,7 @@ extern "C" nxc_status nxc_reduce(nxc_ctx *ctx, int op, const nxc_tensor *out, co
       if (s) goto fail;
       return NXC_OK;
     }
-    nxc_status st = NXC_ERR_UNSUPPORTED_DTYPE;
-    switch (op) {
-      NXC_RED_CASE(NXC_SUM) NXC_RED_CASE(NXC_PROD) NXC_RED_CASE(NXC_RMAX) NXC_RED_CASE(NXC_RMIN)
-      default: break;
-    }
-    s = st;
+    s = arith ? nxc_reduce_sumprod(ctx, op, dt, p) : nxc_reduce_maxmin(ctx, op, dt, p);
     if (s) goto fail;
     return NXC_OK;
   }

@@ -492,6 +492,9 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   const int64_t items = (p.R + vec - 1) / vec;  // work items per output
   int tl = nxc_log2_ceil(items);
   if (tl > 8) tl = 8;
+  // plenty of rows: keep a row inside one warp (shuffle-only combine, no block barrier) and let
+  // each lane walk the row; many threads per row only pay off when rows are scarce
+  if (tl > 5 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
   a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * 4 * ctx->sm_count) ? 4 : 1;
