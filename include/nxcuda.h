@@ -171,6 +171,20 @@ NXC_API nxc_status nxc_scatter(nxc_ctx *ctx, const nxc_tensor *out, const nxc_te
 NXC_API nxc_status nxc_threefry(nxc_ctx *ctx, const nxc_tensor *out_i32, const nxc_tensor *key_i32,
                         const nxc_tensor *ctr_i32);
 
+/* replaces caml_nx_c_sort / caml_nx_c_argsort (reference: nx_c_sort.c:476-514). NaN-class
+   elements last in both directions; complex lexicographic; argsort stable, int32 result. */
+NXC_API nxc_status nxc_sort(nxc_ctx *ctx, int is_argsort, const nxc_tensor *out, const nxc_tensor *in, int axis,
+                            int descending);
+
+/* replaces caml_nx_c_unfold / caml_nx_c_fold (reference: nx_c_move.c:588-870): im2col / col2im
+   over the trailing K spatial dims; padding_flat = [before0, after0, before1, ...]. */
+NXC_API nxc_status nxc_unfold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int K,
+                              const int64_t *kernel, const int64_t *stride, const int64_t *dilation,
+                              const int64_t *padding_flat);
+NXC_API nxc_status nxc_fold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int K,
+                            const int64_t *output_size, const int64_t *kernel, const int64_t *stride,
+                            const int64_t *dilation, const int64_t *padding_flat);
+
 /* ---- multi-GPU exchange (new; the reference has no collective in the
    backend contract -- SURVEY.md section 8e). One process per GPU; NCCL is
    dlopen'ed (libnccl.so.2) so the library loads without it. ------------------ */

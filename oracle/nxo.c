@@ -1081,6 +1081,125 @@ nxo_status nxo_scatter(const nxo_tensor *out, const nxo_tensor *idx, const nxo_t
   return NULL;
 }
 
+/* ==== unfold / fold (nx_c_move.c:588-870) =================================================
+   Window geometry: per spatial dim, win = max(1, (extent + pad_before + pad_after - eff) / stride + 1)
+   with eff = dilation * (kernel - 1) + 1 (nx_c_move.c:632-646). Restated in the FORWARD direction:
+   walk (leading, kernel offset, window) and visit the one source position each pair names.
+     unfold  copies that position into out[lead, kf, wf], or zero when it falls in the padding
+             (nx_c_move.c:660-696).
+     fold    adds in[lead, kf, wf] into a compute-typed accumulator of that position. kf is the
+             OUTER loop, so every output still receives its taps in ascending-kf order -- the
+             order the reference's per-output gather sums them in (nx_c_move.c:755-790) -- and
+             the accumulator is rounded to storage once, at the end. */
+typedef struct {
+  int K;
+  int64_t kernel[NXO_MAX_NDIM], stride[NXO_MAX_NDIM], dil[NXO_MAX_NDIM], before[NXO_MAX_NDIM];
+  int64_t extent[NXO_MAX_NDIM], win[NXO_MAX_NDIM];
+  int64_t kprod, nwin, nspatial;
+} wgeom;
+static nxo_status wgeom_init(wgeom *g, int K, const int64_t *extent, const int64_t *kernel, const int64_t *stride,
+                             const int64_t *dil, const int64_t *pad) {
+  if (K < 1 || K > NXO_MAX_NDIM) return E_SHAPE;
+  g->K = K; g->kprod = 1; g->nwin = 1; g->nspatial = 1;
+  for (int d = 0; d < K; d++) {
+    g->kernel[d] = kernel[d]; g->stride[d] = stride[d]; g->dil[d] = dil[d]; g->before[d] = pad[2 * d];
+    g->extent[d] = extent[d];
+    int64_t span = dil[d] * (kernel[d] - 1) + 1, w = (extent[d] + pad[2 * d] + pad[2 * d + 1] - span) / stride[d] + 1;
+    g->win[d] = w < 1 ? 1 : w;
+    g->kprod *= kernel[d]; g->nwin *= g->win[d]; g->nspatial *= extent[d];
+  }
+  return NULL;
+}
+/* position (row-major over extent) named by kernel offset kc and window wc, or -1 in the padding;
+   *off gets the strided element offset over `strides` */
+static int64_t wgeom_pos(const wgeom *g, const int64_t *kc, const int64_t *wc, const int64_t *strides, int64_t *off) {
+  int64_t lin = 0;
+  *off = 0;
+  for (int d = 0; d < g->K; d++) {
+    int64_t sp = wc[d] * g->stride[d] + kc[d] * g->dil[d] - g->before[d];
+    if (sp < 0 || sp >= g->extent[d]) return -1;
+    lin = lin * g->extent[d] + sp;
+    *off += sp * strides[d];
+  }
+  return lin;
+}
+static void unravel_rm(int64_t lin, int n, const int64_t *shape, int64_t *coord) {
+  for (int d = n - 1; d >= 0; d--) { coord[d] = shape[d] ? lin % shape[d] : 0; if (shape[d]) lin /= shape[d]; }
+}
+nxo_status nxo_unfold(const nxo_tensor *out, const nxo_tensor *in, int K, const int64_t *kernel,
+                      const int64_t *stride, const int64_t *dil, const int64_t *pad) {
+  nxo_status s;
+  if ((s = chk(out)) || (s = chk(in))) return s;
+  if (DT_CAT[out->dtype] & CAT_PACKED) return E_PACKED;
+  if (K < 1 || in->ndim < K) return E_SHAPE;
+  int ld = in->ndim - K;
+  wgeom g;
+  if ((s = wgeom_init(&g, K, &in->shape[ld], kernel, stride, dil, pad))) return s;
+  int64_t es = DT_SIZE[out->dtype], nlead = 1, kp = out->shape[ld], L = out->shape[ld + 1];
+  for (int d = 0; d < ld; d++) nlead *= in->shape[d];
+  int64_t lc[NXO_MAX_NDIM], kc[NXO_MAX_NDIM], wc[NXO_MAX_NDIM];
+  for (int64_t l = 0; l < nlead; l++) {
+    unravel_rm(l, ld, in->shape, lc);
+    int64_t ibase = in->offset, obase = out->offset;
+    for (int d = 0; d < ld; d++) { ibase += lc[d] * in->strides[d]; obase += lc[d] * out->strides[d]; }
+    for (int64_t kf = 0; kf < kp; kf++) {
+      unravel_rm(kf, K, g.kernel, kc);
+      for (int64_t wf = 0; wf < L; wf++) {
+        unravel_rm(wf, K, g.win, wc);
+        int64_t off;
+        char *dst = (char *)out->data + (obase + kf * out->strides[ld] + wf * out->strides[ld + 1]) * es;
+        if (wgeom_pos(&g, kc, wc, &in->strides[ld], &off) < 0) memset(dst, 0, (size_t)es);
+        else memcpy(dst, (const char *)in->data + (ibase + off) * es, (size_t)es);
+      }
+    }
+  }
+  return NULL;
+}
+nxo_status nxo_fold(const nxo_tensor *out, const nxo_tensor *in, int K, const int64_t *output_size,
+                    const int64_t *kernel, const int64_t *stride, const int64_t *dil, const int64_t *pad) {
+  nxo_status s;
+  if ((s = chk(out)) || (s = chk(in))) return s;
+  int dt = out->dtype;
+  if (DT_CAT[dt] & CAT_PACKED) return E_PACKED;
+  if (K < 1 || in->ndim < 2) return E_SHAPE;
+  int nl = in->ndim - 2;
+  wgeom g;
+  if ((s = wgeom_init(&g, K, output_size, kernel, stride, dil, pad))) return s;
+  int64_t es = DT_SIZE[dt], nlead = 1, kp = in->shape[nl];
+  for (int d = 0; d < nl; d++) nlead *= in->shape[d];
+  if (nlead * g.nspatial == 0) return NULL;
+  /* the reference trusts the frontend here and would read past the column tensor; the
+     restatement (and the device engine) refuse instead */
+  if (in->shape[nl + 1] != g.nwin || kp != g.kprod) return E_SHAPE;
+  val *acc = (val *)malloc(sizeof(val) * (size_t)g.nspatial);
+  int64_t lc[NXO_MAX_NDIM], kc[NXO_MAX_NDIM], wc[NXO_MAX_NDIM], oc[NXO_MAX_NDIM];
+  for (int64_t l = 0; l < nlead; l++) {
+    unravel_rm(l, nl, in->shape, lc);
+    int64_t ibase = in->offset, obase = out->offset;
+    for (int d = 0; d < nl; d++) { ibase += lc[d] * in->strides[d]; obase += lc[d] * out->strides[d]; }
+    memset(acc, 0, sizeof(val) * (size_t)g.nspatial);
+    for (int64_t kf = 0; kf < kp; kf++) {
+      unravel_rm(kf, K, g.kernel, kc);
+      for (int64_t wf = 0; wf < g.nwin; wf++) {
+        unravel_rm(wf, K, g.win, wc);
+        int64_t off, pos = wgeom_pos(&g, kc, wc, &out->strides[nl], &off);
+        if (pos < 0) continue;
+        val v = ld(dt, (const char *)in->data + (ibase + kf * in->strides[nl] + wf * in->strides[nl + 1]) * es);
+        if (DT_KIND[dt] == K_BOOL) acc[pos].b = (uint8_t)(acc[pos].b + v.b); /* uint8_t compute type */
+        else acc[pos] = bin_apply(ADD, dt, acc[pos], v);
+      }
+    }
+    for (int64_t p = 0; p < g.nspatial; p++) {
+      unravel_rm(p, K, g.extent, oc);
+      int64_t off = obase;
+      for (int d = 0; d < K; d++) off += oc[d] * out->strides[nl + d];
+      st(dt, (char *)out->data + off * es, acc[p]);
+    }
+  }
+  free(acc);
+  return NULL;
+}
+
 /* ==== threefry2x32, 20 rounds (nx_c_random.c:44-61; Random123 reference constants) ====== */
 static uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 static void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t *o0, uint32_t *o1) {
@@ -1123,6 +1242,91 @@ nxo_status nxo_threefry(const nxo_tensor *out, const nxo_tensor *key, const nxo_
     *(uint32_t *)o.ptr[0] = r0;
     *(uint32_t *)(o.ptr[0] + so) = r1;
   }
+  return NULL;
+}
+
+
+/* ==== sort / argsort (nx_c_sort.c:47-101, 265-276) ======================================
+   NaN-class elements (any NaN part for complex) last in both directions, in original order;
+   complex lexicographic; argsort stable (value ties keep the first index in either
+   direction). Restated as a merge sort on (value, original index) under that total order. */
+typedef struct { val v; int32_t i; } sort_item;
+static int sort_dt, sort_desc;
+static int sort_isnan(val x) {
+  switch (DT_KIND[sort_dt]) {
+    case K_F32: return isnan(x.f);
+    case K_F64: return isnan(x.d);
+    case K_C32: return isnan(crealf(x.c32)) || isnan(cimagf(x.c32));
+    case K_C64: return isnan(creal(x.c64)) || isnan(cimag(x.c64));
+  }
+  return 0;
+}
+static int sort_lt(val x, val y) {
+  switch (DT_KIND[sort_dt]) {
+    case K_F32: return x.f < y.f;
+    case K_F64: return x.d < y.d;
+    case K_I64: return x.i < y.i;
+    case K_U64: return x.u < y.u;
+    case K_BOOL: return x.b < y.b;
+    case K_C32: return crealf(x.c32) < crealf(y.c32) || (crealf(x.c32) == crealf(y.c32) && cimagf(x.c32) < cimagf(y.c32));
+    case K_C64: return creal(x.c64) < creal(y.c64) || (creal(x.c64) == creal(y.c64) && cimag(x.c64) < cimag(y.c64));
+  }
+  return 0;
+}
+static int sort_before(const sort_item *a, const sort_item *b) {
+  int na = sort_isnan(a->v), nb = sort_isnan(b->v);
+  if (na || nb) return (na && nb) ? a->i < b->i : nb;
+  if (!sort_lt(a->v, b->v) && !sort_lt(b->v, a->v)) return a->i < b->i;
+  return sort_desc ? sort_lt(b->v, a->v) : sort_lt(a->v, b->v);
+}
+static void sort_merge(sort_item *a, sort_item *tmp, int64_t n) {
+  if (n < 2) return;
+  int64_t h = n / 2;
+  sort_merge(a, tmp, h);
+  sort_merge(a + h, tmp, n - h);
+  int64_t i = 0, j = h, k = 0;
+  while (i < h && j < n) tmp[k++] = sort_before(&a[j], &a[i]) ? a[j++] : a[i++];
+  while (i < h) tmp[k++] = a[i++];
+  while (j < n) tmp[k++] = a[j++];
+  memcpy(a, tmp, (size_t)n * sizeof *a);
+}
+nxo_status nxo_sort(int is_arg, const nxo_tensor *out, const nxo_tensor *in, int axis, int desc) {
+  nxo_status s;
+  if ((s = chk(in)) || (s = chk(out))) return s;
+  int dt = in->dtype;
+  if (DT_CAT[dt] & CAT_PACKED) return E_PACKED;
+  if (axis < 0 || axis >= in->ndim) return E_AXIS;
+  if (out->ndim != in->ndim) return E_OUT_RANK;
+  int64_t es = DT_SIZE[dt], oes = is_arg ? 4 : es, len = in->shape[axis];
+  int nk = 0;
+  int64_t ks[NXO_MAX_NDIM], kin[NXO_MAX_NDIM], kout[NXO_MAX_NDIM], O = 1;
+  for (int a = 0; a < in->ndim; a++) {
+    if (a == axis) continue;
+    ks[nk] = in->shape[a]; kin[nk] = in->strides[a] * es; kout[nk] = out->strides[a] * oes; O *= in->shape[a]; nk++;
+  }
+  if (O == 0 || len == 0) return NULL;
+  for (int a = 0; a < in->ndim; a++) if (in->shape[a] > 1 && out->strides[a] == 0) return E_ALIASED;
+  sort_item *buf = malloc((size_t)len * sizeof *buf * 2);
+  if (!buf) return "out of memory";
+  sort_dt = dt; sort_desc = desc;
+  const char *ip = (const char *)in->data + in->offset * es;
+  char *opp = (char *)out->data + out->offset * oes;
+  int64_t kc[NXO_MAX_NDIM] = {0}, ai = in->strides[axis] * es, ao = out->strides[axis] * oes;
+  for (int64_t o = 0; o < O; o++) {
+    for (int64_t k = 0; k < len; k++) { buf[k].v = ld(dt, ip + k * ai); buf[k].i = (int32_t)k; }
+    sort_merge(buf, buf + len, len);
+    for (int64_t k = 0; k < len; k++) {
+      if (is_arg) *(int32_t *)(opp + k * ao) = buf[k].i;
+      else memcpy(opp + k * ao, ip + buf[k].i * ai, (size_t)es);
+    }
+    for (int d = nk - 1; d >= 0; d--) {
+      if (++kc[d] < ks[d]) { ip += kin[d]; opp += kout[d]; break; }
+      kc[d] = 0;
+      ip -= (ks[d] - 1) * kin[d];
+      opp -= (ks[d] - 1) * kout[d];
+    }
+  }
+  free(buf);
   return NULL;
 }
 

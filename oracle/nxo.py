@@ -52,7 +52,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(LIB_PATH)
         for n in ("nxo_map1 nxo_map2 nxo_cmp nxo_where nxo_copy nxo_cast nxo_reduce nxo_argreduce nxo_scan "
-                  "nxo_matmul nxo_pad nxo_cat nxo_gather nxo_scatter nxo_threefry nxo_fill").split():
+                  "nxo_matmul nxo_pad nxo_cat nxo_gather nxo_scatter nxo_threefry nxo_fill nxo_sort nxo_unfold nxo_fold").split():
             getattr(_lib, n).restype = ctypes.c_char_p
         _lib.nxo_status_is_invalid_argument.argtypes = [ctypes.c_char_p]
     return _lib
@@ -189,7 +189,43 @@ def scatter(template, indices, updates, axis, mode):
     return out
 
 
+def _i64(xs):
+    return (ctypes.c_int64 * max(len(xs), 1))(*[int(v) for v in xs])
+
+
+def unfold(x, kernel_size, stride, dilation, padding):
+    k = len(kernel_size)
+    ld = len(x.shape) - k
+    sp = x.shape[ld:]
+    # OCaml's `/` truncates toward zero (a kernel wider than the padded extent gives 0 or 1 windows)
+    osp = [int(((sp[i] + padding[i][0] + padding[i][1]) - (dilation[i] * (kernel_size[i] - 1) + 1)) / stride[i]) + 1
+           for i in range(k)]
+    out = HostView.empty(x.dtype, list(x.shape[:ld]) + [int(np.prod(kernel_size)), int(np.prod(osp))])
+    _chk("unfold", lib().nxo_unfold(ctypes.byref(_d(out)), ctypes.byref(_d(x)), k, _i64(kernel_size), _i64(stride),
+                                    _i64(dilation), _i64([v for p in padding for v in p])))
+    return out
+
+
+def fold(x, output_size, kernel_size, stride, dilation, padding):
+    out = HostView.empty(x.dtype, list(x.shape[:len(x.shape) - 2]) + list(output_size))
+    _chk("fold", lib().nxo_fold(ctypes.byref(_d(out)), ctypes.byref(_d(x)), len(kernel_size), _i64(output_size),
+                                _i64(kernel_size), _i64(stride), _i64(dilation), _i64([v for p in padding for v in p])))
+    return out
+
+
 def threefry(key, ctr):
     out = HostView.empty("i32", ctr.shape)
     _chk("threefry", lib().nxo_threefry(ctypes.byref(_d(out)), ctypes.byref(_d(key)), ctypes.byref(_d(ctr))))
+    return out
+
+
+def sort(x, axis, descending=False):
+    out = HostView.empty(x.dtype, x.shape)
+    _chk("sort", lib().nxo_sort(0, ctypes.byref(_d(out)), ctypes.byref(_d(x)), int(axis), 1 if descending else 0))
+    return out
+
+
+def argsort(x, axis, descending=False):
+    out = HostView.empty("i32", x.shape)
+    _chk("argsort", lib().nxo_sort(1, ctypes.byref(_d(out)), ctypes.byref(_d(x)), int(axis), 1 if descending else 0))
     return out

@@ -248,6 +248,25 @@ def scatter(template, indices, updates, axis, mode) -> HostView:
     return out
 
 
+def unfold(x, kernel_size, stride, dilation, padding) -> HostView:
+    k = len(kernel_size)
+    ld = len(x.shape) - k
+    sp = x.shape[ld:]
+    # OCaml's `/` truncates toward zero (a kernel wider than the padded extent gives 0 or 1 windows)
+    osp = [int(((sp[i] + padding[i][0] + padding[i][1]) - (dilation[i] * (kernel_size[i] - 1) + 1)) / stride[i]) + 1
+           for i in range(k)]
+    out = HostView.empty(x.dtype, list(x.shape[:ld]) + [int(np.prod(kernel_size)), int(np.prod(osp))])
+    call("unfold", out, x, list(kernel_size), list(stride), list(dilation), [v for p in padding for v in p])
+    return out
+
+
+def fold(x, output_size, kernel_size, stride, dilation, padding) -> HostView:
+    out = HostView.empty(x.dtype, list(x.shape[:len(x.shape) - 2]) + list(output_size))
+    call("fold", out, x, list(output_size), list(kernel_size), list(stride), list(dilation),
+         [v for p in padding for v in p])
+    return out
+
+
 def threefry(key, ctr) -> HostView:
     out = HostView.empty("i32", ctr.shape)
     call("threefry", out, key, ctr)

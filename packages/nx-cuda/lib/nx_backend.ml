@@ -178,6 +178,45 @@ let threefry key counter =
   caml_threefry out key counter;
   out
 
+(* ---- sort family ---- *)
+external caml_sort : bool -> ('c, 'd) t -> ('a, 'b) t -> int -> bool -> unit = "nx_cuda_sort"
+
+let sort ~axis ~descending x =
+  let out = create_tensor x.context x.dtype x.shape in
+  caml_sort false out x axis descending;
+  out
+
+let argsort ~axis ~descending x =
+  let out = create_tensor x.context Dtype.Int32 x.shape in
+  caml_sort true out x axis descending;
+  out
+
+(* ---- window ops (im2col / col2im) ---- *)
+external caml_unfold : ('a, 'b) t -> ('a, 'b) t -> int array -> int array -> int array -> int array -> unit
+  = "nx_cuda_unfold_bc" "nx_cuda_unfold"
+external caml_fold : ('a, 'b) t -> ('a, 'b) t -> int array -> int array -> int array -> int array -> int array -> unit
+  = "nx_cuda_fold_bc" "nx_cuda_fold"
+
+let flat_pairs p = Array.concat (Array.to_list (Array.map (fun (b, a) -> [| b; a |]) p))
+
+let unfold x ~kernel_size ~stride ~dilation ~padding =
+  let k = Array.length kernel_size in
+  let nlead = Array.length x.shape - k in
+  let windows i =
+    let before, after = padding.(i) in
+    ((x.shape.(nlead + i) + before + after - (dilation.(i) * (kernel_size.(i) - 1) + 1)) / stride.(i)) + 1 in
+  let l = Array.fold_left ( * ) 1 (Array.init k windows) in
+  let kp = Array.fold_left ( * ) 1 kernel_size in
+  let out = create_tensor x.context x.dtype (Array.append (Array.sub x.shape 0 nlead) [| kp; l |]) in
+  caml_unfold out x kernel_size stride dilation (flat_pairs padding);
+  out
+
+let fold x ~output_size ~kernel_size ~stride ~dilation ~padding =
+  let nlead = Array.length x.shape - 2 in
+  let out = create_tensor x.context x.dtype (Array.append (Array.sub x.shape 0 nlead) output_size) in
+  caml_fold out x output_size kernel_size stride dilation (flat_pairs padding);
+  out
+
 (* ---- matmul ---- *)
 external caml_matmul : ('a, 'b) t -> ('a, 'b) t -> ('a, 'b) t -> unit = "nx_cuda_matmul"
 
@@ -193,12 +232,8 @@ let matmul x y =
   caml_matmul out x y;
   out
 
-(* ---- not yet behind the C ABI (scope table 8f ranks 2 and 4): fail loudly, never fall back ---- *)
+(* ---- not yet behind the C ABI (scope table 8f rank 4): fail loudly, never fall back ---- *)
 let todo op = failwith (op ^ ": not implemented by nx-cuda")
-let sort ~axis:_ ~descending:_ _ = todo "sort"
-let argsort ~axis:_ ~descending:_ _ = todo "argsort"
-let unfold _ ~kernel_size:_ ~stride:_ ~dilation:_ ~padding:_ = todo "unfold"
-let fold _ ~output_size:_ ~kernel_size:_ ~stride:_ ~dilation:_ ~padding:_ = todo "fold"
 let fft _ ~axes:_ = todo "fft"
 let ifft _ ~axes:_ = todo "ifft"
 let rfft _ ~dtype:_ ~axes:_ = todo "rfft"

@@ -232,3 +232,44 @@ CAMLprim value nx_cuda_threefry(value vout, value vkey, value vctr) {
   if (s) raise_status("threefry", CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
+static void ints_of_value(value v, int64_t *dst, int cap) {
+  int n = (int)Wosize_val(v);
+  for (int i = 0; i < n && i < cap; i++) dst[i] = Long_val(Field(v, i));
+}
+CAMLprim value nx_cuda_unfold(value vout, value vin, value vk, value vs, value vd, value vp) {
+  CAMLparam5(vout, vin, vk, vs, vd);
+  CAMLxparam1(vp);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int64_t k[NXC_MAX_NDIM], st[NXC_MAX_NDIM], d[NXC_MAX_NDIM], p[2 * NXC_MAX_NDIM];
+  ints_of_value(vk, k, NXC_MAX_NDIM); ints_of_value(vs, st, NXC_MAX_NDIM);
+  ints_of_value(vd, d, NXC_MAX_NDIM); ints_of_value(vp, p, 2 * NXC_MAX_NDIM);
+  nxc_status s = nxc_unfold(CTX_OF(vout), &o, &a, (int)Wosize_val(vk), k, st, d, p);
+  if (s) raise_status("unfold", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_unfold_bc(value *argv, int argn) {
+  (void)argn;
+  return nx_cuda_unfold(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+CAMLprim value nx_cuda_fold(value vout, value vin, value vsz, value vk, value vs, value vd, value vp) {
+  CAMLparam5(vout, vin, vsz, vk, vs);
+  CAMLxparam2(vd, vp);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int64_t sz[NXC_MAX_NDIM], k[NXC_MAX_NDIM], st[NXC_MAX_NDIM], d[NXC_MAX_NDIM], p[2 * NXC_MAX_NDIM];
+  ints_of_value(vsz, sz, NXC_MAX_NDIM); ints_of_value(vk, k, NXC_MAX_NDIM); ints_of_value(vs, st, NXC_MAX_NDIM);
+  ints_of_value(vd, d, NXC_MAX_NDIM); ints_of_value(vp, p, 2 * NXC_MAX_NDIM);
+  nxc_status s = nxc_fold(CTX_OF(vout), &o, &a, (int)Wosize_val(vk), sz, k, st, d, p);
+  if (s) raise_status("fold", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_fold_bc(value *argv, int argn) {
+  (void)argn;
+  return nx_cuda_fold(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]);
+}
+CAMLprim value nx_cuda_sort(value varg, value vout, value vin, value vaxis, value vdesc) {
+  CAMLparam5(varg, vout, vin, vaxis, vdesc);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  nxc_status s = nxc_sort(CTX_OF(vout), Bool_val(varg), &o, &a, Int_val(vaxis), Bool_val(vdesc));
+  if (s) raise_status(Bool_val(varg) ? "argsort" : "sort", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}

@@ -74,6 +74,9 @@ SYMBOLS = {
     "nxc_gather": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_scatter": (_S, [_P, _T, _T, _T, ctypes.c_int, ctypes.c_int]),
     "nxc_threefry": (_S, [_P, _T, _T, _T]),
+    "nxc_unfold": (_S, [_P, _T, _T, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int64)] * 4),
+    "nxc_fold": (_S, [_P, _T, _T, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int64)] * 5),
+    "nxc_sort": (_S, [_P, ctypes.c_int, _T, _T, ctypes.c_int, ctypes.c_int]),
     "nxc_dist_unique_id": (_S, [_P]),
     "nxc_dist_init": (_S, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "nxc_dist_finalize": (_S, [_P]),

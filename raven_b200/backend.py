@@ -450,6 +450,59 @@ def associative_scan(x: Tensor, axis: int, op: str) -> Tensor:
     return out
 
 
+# ---- window ops (backend_c/nx_backend.ml:418-464) ------------------------------------------
+def _i64(xs):
+    return (ctypes.c_int64 * _b.max(len(xs), 1))(*[int(v) for v in xs])
+
+
+def unfold(x: Tensor, kernel_size, stride, dilation, padding) -> Tensor:
+    k = len(kernel_size)
+    lead_nd = len(x.shape) - k
+    leading, spatial = list(x.shape[:lead_nd]), x.shape[lead_nd:]
+    # OCaml's `/` truncates toward zero (a kernel wider than the padded extent gives 0 or 1 windows)
+    out_spatial = [int(((spatial[i] + padding[i][0] + padding[i][1]) - (dilation[i] * (kernel_size[i] - 1) + 1))
+                       / stride[i]) + 1 for i in range(k)]
+    kp, l = 1, 1
+    for v in kernel_size:
+        kp *= v
+    for v in out_spatial:
+        l *= v
+    out = _create(x.context, x.dtype, leading + [kp, l])
+    flat = [v for pr in padding for v in pr]
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "unfold", x.context._lib.nxc_unfold, ctypes.byref(do), ctypes.byref(dx), k, _i64(kernel_size),
+          _i64(stride), _i64(dilation), _i64(flat))
+    return out
+
+
+def fold(x: Tensor, output_size, kernel_size, stride, dilation, padding) -> Tensor:
+    k = len(kernel_size)
+    leading = list(x.shape[:len(x.shape) - 2])
+    out = _create(x.context, x.dtype, leading + list(output_size))
+    flat = [v for pr in padding for v in pr]
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "fold", x.context._lib.nxc_fold, ctypes.byref(do), ctypes.byref(dx), k, _i64(output_size),
+          _i64(kernel_size), _i64(stride), _i64(dilation), _i64(flat))
+    return out
+
+
+# ---- sort family (backend_c/nx_backend.ml:321-338) ---------------------------------------
+def sort(x: Tensor, axis: int, descending: bool = False) -> Tensor:
+    out = _create(x.context, x.dtype, x.shape)
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "sort", x.context._lib.nxc_sort, 0, ctypes.byref(do), ctypes.byref(dx), int(axis),
+          1 if descending else 0)
+    return out
+
+
+def argsort(x: Tensor, axis: int, descending: bool = False) -> Tensor:
+    out = _create(x.context, _dt.int32, x.shape)
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "argsort", x.context._lib.nxc_sort, 1, ctypes.byref(do), ctypes.byref(dx), int(axis),
+          1 if descending else 0)
+    return out
+
+
 # ---- matmul (backend_c/nx_backend.ml:485-500) ---------------------------------------------
 def matmul(x: Tensor, y: Tensor) -> Tensor:
     xs, ys = x.shape, y.shape

@@ -494,7 +494,7 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   if (tl > 8) tl = 8;
   // plenty of rows: keep a row inside one warp (shuffle-only combine, no block barrier) and let
   // each lane walk the row; many threads per row only pay off when rows are scarce
-  if (tl > 5 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
+  if (tl > 5 && items <= 512 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
   a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * 4 * ctx->sm_count) ? 4 : 1;

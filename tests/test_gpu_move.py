@@ -9,6 +9,7 @@ import pytest
 
 import raven_b200.backend as B
 from raven_b200 import Failure, InvalidArgument
+from raven_b200 import dtype as DT
 from tests import harness as H
 from tests.test_gpu_map import _rand
 
@@ -178,6 +179,92 @@ def test_packed_int4(ctx, oracle, pk):
     assert B.to_host(base).tolist() == [0x21, 0x43, 0xF5, 0xFF]
     strided = B.permute(_dev_packed(ctx, H.HostView(np.zeros(8, np.uint8), pk, [4, 4])), [1, 0])
     with pytest.raises(Failure, match="cast: packed dtype not supported for this operation"):
-        B.cast(strided, D.float32)
+        B.cast(strided, DT.float32)
     with pytest.raises(Failure, match="add: packed dtype not supported for this operation"):
         B.add(base, base)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "bf16", "f16", "i32", "u8", "i64", "u32", "bool", "c32"])
+def test_sort_argsort(ctx, oracle, dt):
+    """sort / argsort vs the oracle: NaN last both ways, stable argsort (bit-exact indices),
+    complex lexicographic; short axes (several slices per shared-memory chunk), a 5000-long
+    axis (global bitonic stages), strided and flipped inputs."""
+    rng = np.random.default_rng(5)
+    cases = [hv for _, hv in H.layouts(dt, include_degenerate=False)]
+    n = 3 * 5000
+    if dt in H.FLOATS:
+        v = np.round(rng.uniform(-50, 50, n))
+        v[rng.integers(0, n, 40)] = np.nan
+        data = H.to_storage(dt, v)
+    elif dt in H.COMPLEX:
+        data = (np.round(rng.uniform(-3, 3, n)) + 1j * np.round(rng.uniform(-3, 3, n))).astype(H.np_storage(dt))
+        data[[7, 4000]] = complex(np.nan, 1)
+    elif dt == "bool":
+        data = rng.integers(0, 2, n).astype(np.uint8)
+    else:
+        data = (_rand(dt, n, rng) % 97).astype(H.np_storage(dt))
+    big = H.HostView(data, dt, [3, 5000])
+    cases += [big, big.permute([1, 0]), big.flip([1]), H.HostView(data[:4096].copy(), dt, [2, 2048])]
+    for hv in cases:
+        for axis in range(len(hv.shape)):
+            for desc in (False, True):
+                want = oracle.argsort(hv, axis, desc).numpy()
+                got = H.download(B.argsort(H.upload(ctx, hv), axis, desc))
+                assert np.array_equal(got, want), f"argsort/{dt}/{hv.shape}/{axis}/{desc}"
+                want = oracle.sort(hv, axis, desc).numpy()
+                got = H.download(B.sort(H.upload(ctx, hv), axis, desc))
+                if dt in H.COMPLEX:
+                    assert np.array_equal(got, want, equal_nan=True) or np.array_equal(np.isnan(got), np.isnan(want))
+                else:
+                    assert np.array_equal(H.storage_to_float(dt, got), H.storage_to_float(dt, want), equal_nan=True), \
+                        f"sort/{dt}/{hv.shape}/{axis}/{desc}"
+
+
+WINDOW_CASES = [
+    # (leading, spatial, kernel, stride, dilation, padding)
+    ([2, 3], [7], [3], [1], [1], [(0, 0)]),
+    ([2], [8], [3], [2], [2], [(1, 2)]),
+    ([1, 2], [6, 5], [3, 2], [1, 1], [1, 1], [(0, 0), (0, 0)]),
+    ([2, 2], [7, 6], [3, 3], [2, 1], [1, 2], [(1, 1), (2, 0)]),
+    ([], [5, 4, 3], [2, 2, 2], [1, 2, 1], [1, 1, 1], [(0, 1), (1, 0), (0, 0)]),
+    ([3], [4], [5], [1], [1], [(0, 0)]),
+    ([4, 8], [32, 32], [3, 3], [1, 1], [1, 1], [(1, 1), (1, 1)]),   # a LeNet/ResNet-style 3x3 same conv
+    ([2, 4], [28, 28], [5, 5], [2, 2], [1, 1], [(2, 2), (2, 2)]),
+]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "bf16", "f16", "f8e4m3", "i8", "i32", "u8", "i64", "u64", "bool", "c32", "c64"])
+def test_unfold_fold(ctx, oracle, dt):
+    """im2col / col2im vs the oracle, bit for bit (fold sums taps in the reference's order, so
+    floats are exact too); contiguous and permuted inputs, padding, stride, dilation, K=1..3."""
+    rng = np.random.default_rng(11)
+    for lead, sp, k, s, d, p in WINDOW_CASES:
+        shape = lead + sp
+        n = int(np.prod(shape))
+        x = H.HostView(_rand(dt, n, rng), dt, shape)
+        want = oracle.unfold(x, k, s, d, p)
+        got = B.unfold(H.upload(ctx, x), k, s, d, p)
+        assert tuple(got.shape) == tuple(want.shape)
+        assert np.array_equal(H.raw(H.download(got)), H.raw(want.numpy())), f"unfold/{dt}/{shape}/{k}"
+        if want.shape[-1] > 0:
+            w2 = oracle.fold(want, sp, k, s, d, p)
+            g2 = B.fold(got, sp, k, s, d, p)
+            assert np.array_equal(H.raw(H.download(g2)), H.raw(w2.numpy())), f"fold/{dt}/{shape}/{k}"
+        if len(shape) >= 2:
+            perm = list(range(len(shape)))[::-1]
+            xp = H.HostView(_rand(dt, n, rng), dt, shape[::-1]).permute(perm)
+            if list(xp.shape) == shape:
+                want = oracle.unfold(xp, k, s, d, p)
+                got = B.unfold(H.upload(ctx, xp), k, s, d, p)
+                assert np.array_equal(H.raw(H.download(got)), H.raw(want.numpy())), f"unfold-strided/{dt}/{shape}"
+
+
+def test_unfold_fold_errors(ctx):
+    x = B.full(ctx, DT.float32, [2, 3, 8], 1.0)
+    cols = B.unfold(x, [3], [1], [1], [(0, 0)])
+    assert tuple(cols.shape) == (2, 3, 3, 6)
+    with pytest.raises(InvalidArgument, match="fold: shape mismatch"):
+        B.fold(cols, [9], [3], [1], [1], [(0, 0)])   # 9 - 3 + 1 = 7 windows, the columns hold 6
+    p = B.buffer(ctx, DT.int4, [8])
+    with pytest.raises(Failure, match="unfold: packed dtype"):
+        B.unfold(p, [2], [1], [1], [(0, 0)])

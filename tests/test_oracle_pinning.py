@@ -244,3 +244,78 @@ def test_packed_int4_matches_reference():
         strided = H.HostView(np.zeros(8, np.uint8), pk, [4, 4]).permute([1, 0])
         r, o = _both(lambda m: m.cast(strided, "f32"))
         assert isinstance(r, tuple) and r == o and "packed" in r[2]
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_sort_argsort_match_reference(dt):
+    """sort / argsort: NaN last in both directions, stable argsort, complex lexicographic
+    (nx_c_sort.c). Value sort is compared numerically (equal keys -- +0/-0, NaN payloads --
+    are interchangeable there, as the reference documents); argsort exactly."""
+    rng = np.random.default_rng(5)
+    cases = [hv for _, hv in H.layouts(dt, include_degenerate=False)]
+    if dt in H.FLOATS:
+        v = np.round(rng.uniform(-5, 5, 200))
+        v[[3, 50, 120]] = np.nan
+        cases.append(H.HostView(H.to_storage(dt, v), dt, [10, 20]))
+    elif dt in H.COMPLEX:
+        v = (np.round(rng.uniform(-3, 3, 200)) + 1j * np.round(rng.uniform(-3, 3, 200))).astype(H.np_storage(dt))
+        v[7] = complex(np.nan, 1)
+        cases.append(H.HostView(v, dt, [10, 20]))
+    else:
+        from tests.test_gpu_map import _rand
+        cases.append(H.HostView(_rand(dt, 200, rng) if dt == "bool" else (_rand(dt, 200, rng) % 7).astype(H.np_storage(dt)), dt, [10, 20]))
+    for hv in cases:
+        for axis in range(len(hv.shape)):
+            for desc in (False, True):
+                r, o = _both(lambda m: m.argsort(hv, axis, desc))
+                _same("i32", r, o, f"argsort/{dt}/{hv.shape}/{axis}/{desc}")
+                r, o = _both(lambda m: m.sort(hv, axis, desc))
+                x, y = o.numpy(), r.numpy()
+                if dt in H.COMPLEX:
+                    assert np.array_equal(x, y, equal_nan=True) or np.array_equal(np.isnan(x), np.isnan(y))
+                else:
+                    fx, fy = H.storage_to_float(dt, x), H.storage_to_float(dt, y)
+                    assert np.array_equal(fx, fy, equal_nan=True), f"sort/{dt}/{hv.shape}/{axis}/{desc}"
+
+
+WINDOW_CASES = [
+    # (leading, spatial, kernel, stride, dilation, padding)
+    ([2, 3], [7], [3], [1], [1], [(0, 0)]),
+    ([2], [8], [3], [2], [2], [(1, 2)]),
+    ([1, 2], [6, 5], [3, 2], [1, 1], [1, 1], [(0, 0), (0, 0)]),
+    ([2, 2], [7, 6], [3, 3], [2, 1], [1, 2], [(1, 1), (2, 0)]),
+    ([], [5, 4, 3], [2, 2, 2], [1, 2, 1], [1, 1, 1], [(0, 1), (1, 0), (0, 0)]),
+    ([3], [4], [5], [1], [1], [(0, 0)]),   # kernel larger than the extent: win clamps to 1
+]
+
+
+@pytest.mark.parametrize("dt", ALL)
+def test_unfold_fold_match_reference(dt):
+    """im2col / col2im (nx_c_move.c:588-870): padded taps read zero; fold sums overlapping taps in
+    the compute type in ascending kernel-offset order -- compared bit for bit, floats included."""
+    from tests.test_gpu_map import _rand
+    rng = np.random.default_rng(11)
+    for lead, sp, k, s, d, p in WINDOW_CASES:
+        shape = lead + sp
+        n = int(np.prod(shape))
+        x = H.HostView(_rand(dt, n, rng), dt, shape)
+        r, o = _both(lambda m: m.unfold(x, k, s, d, p))
+        _same(dt, r, o, f"unfold/{dt}/{shape}/{k}")
+        cols = o
+        if cols.shape[-1] > 0:  # L == 0 with a clamped window count is undefined in the reference
+            r, o = _both(lambda m: m.fold(cols, sp, k, s, d, p))
+            _same(dt, r, o, f"fold/{dt}/{shape}/{k}")
+        if len(shape) >= 2:  # a permuted (strided) input
+            xp = H.HostView(_rand(dt, n, rng), dt, shape[::-1]).permute(list(range(len(shape)))[::-1])
+            if list(xp.shape) == shape:
+                r, o = _both(lambda m: m.unfold(xp, k, s, d, p))
+                _same(dt, r, o, f"unfold-strided/{dt}/{shape}/{k}")
+    x = H.HostView(_rand(dt, 0, rng), dt, [0, 5])
+    r, o = _both(lambda m: m.unfold(x, [2], [1], [1], [(0, 0)]))
+    _same(dt, r, o, "unfold-empty")
+
+
+def test_unfold_fold_packed_rejected():
+    x = H.HostView(np.zeros(4, np.uint8), "i4", [8])
+    r, o = _both(lambda m: m.unfold(x, [2], [1], [1], [(0, 0)]))
+    assert isinstance(r, tuple) and r == o
