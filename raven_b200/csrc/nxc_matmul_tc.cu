@@ -13,6 +13,17 @@
 //   A[m,k], a_rs == 1       M(128 B) x BLOCK_K rows, xN   MN-major, SWIZZLE_128B
 //   B[k,n], b_rs == 1       K(128 B) x 256 rows          K-major
 //   B[k,n], b_cs == 1       N(128 B) x BLOCK_K rows, xN   MN-major
+// An MN-major 32-bit operand uses the 32-byte-atom flavour of the 128-byte swizzle on both
+// the TMA and the descriptor side (layout type 1, 4-row groups): the only swizzled MN-major
+// layout tcgen05 accepts for tf32 -- the plain SWIZZLE_128B one silently yields zeros.
+//
+// Two instantiations of one kernel:
+//   PAIR = false  one CTA per tile, 128x256, tcgen05.mma.cta_group::1 (small M, fallback)
+//   PAIR = true   a 2-CTA cluster (the two SMs of a TPC) per 256x256 tile,
+//                 tcgen05.mma.cta_group::2 issued by the even CTA: each CTA stages its own
+//                 128 rows of A and HALF of B (128 of the 256 columns), so the bytes staged
+//                 per flop drop by a third and 7 stages (instead of 4) fit in shared memory;
+//                 the accumulator rows 0-127 / 128-255 land in each CTA's own TMEM.
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected thread) and
 // TMEM owner, warps 2-5 epilogue (tcgen05.ld -> convert -> 16-byte global stores).
@@ -21,21 +32,27 @@
 // the MMAs of tile i+1), and a static persistent tile schedule that walks N
 // within groups of 8 M-blocks so concurrently resident tiles share A and B in L2.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "nxc_matmul.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int BLOCK_M = 128;    // rows of A (and of the accumulator) one CTA owns
 constexpr int BLOCK_N = 256;
 constexpr int ROW_BYTES = 128;  // one swizzle row: BLOCK_K * esize
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+template <bool PAIR> struct Cfg {
+  static constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;  // rows of C per tile
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;  // rows of B (columns of C) this CTA stages
+  static constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;     // 16 / 32 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = PAIR ? 7 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct TcParams {
   int64_t m, n, k;
@@ -93,13 +110,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // 64-bit shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version bit)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B with 32-byte atoms -- the only
+// swizzled layout tcgen05 accepts for an MN-major 32-bit (tf32) operand
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint64_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version for Blackwell
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= layout << 61;
   return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -123,6 +143,72 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// ---- 2-CTA (cta_group::2) variants ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s counterpart in the even (leader) CTA of the pair
+__device__ __forceinline__ uint32_t leader_addr(const void *p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+// both CTAs of the pair load their own slice; the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once the pair's MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAITC:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONEC;\n\t"
+      "bra LAB_WAITC;\n\t"
+      "LAB_DONEC:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -165,11 +251,14 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int64_t t, int &b
   nb = rr / gsz;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  void *__restrict__ Cout, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  typedef Cfg<PAIR> C;
+  constexpr int STAGES = C::STAGES, B_STAGE_BYTES = C::B_STAGE_BYTES, STAGE_BYTES = C::STAGE_BYTES;
   uint8_t *smem_a = smem;
   uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);
@@ -178,22 +267,34 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int64_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int64_t nworkers = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    // tempty is only waited on by the leader's MMA warp: 4 epilogue warps of each CTA arrive on it
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // the same warp of both CTAs takes part in a cta_group::2 allocation
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -205,37 +306,43 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int elems_per_row = ROW_BYTES / p.esize;  // elements in one 128-byte swizzle row
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t t = worker; t < total_tiles; t += nworkers) {
         int bi, mb, nb;
         tile_coords(p, t, bi, mb, nb);
-        const int m0 = mb * BLOCK_M, n0 = nb * BLOCK_N;
+        const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * BLOCK_N + (int)rank * C::B_ROWS;
         const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
         for (int kb = 0; kb < p.num_kb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          // PAIR: one arrival (the leader's) and the bytes of BOTH CTAs complete the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * STAGE_BYTES);
+          const uint32_t lbar = PAIR ? leader_addr(&full[stage]) : 0u;
           const int k0 = kb * p.block_k;
           uint8_t *sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t *sb = smem_b + stage * B_STAGE_BYTES;
+          auto load = [&](const CUtensorMap *map, void *dst, int c0, int c1, int c2) {
+            if (PAIR) tma_load_3d_pair(map, lbar, dst, c0, c1, c2);
+            else tma_load_3d(map, &full[stage], dst, c0, c1, c2);
+          };
           if (!p.a_mn) {
-            tma_load_3d(&map_a, &full[stage], sa, k0, m0, ba);
+            load(&map_a, sa, k0, m0, ba);
           } else {
             const int box_bytes = p.block_k * ROW_BYTES;
             for (int j = 0; j < BLOCK_M / elems_per_row; j++)
-              tma_load_3d(&map_a, &full[stage], sa + j * box_bytes, m0 + j * elems_per_row, k0, ba);
+              load(&map_a, sa + j * box_bytes, m0 + j * elems_per_row, k0, ba);
           }
           if (!p.b_mn) {
-            tma_load_3d(&map_b, &full[stage], sb, k0, n0, bb);
+            load(&map_b, sb, k0, n0, bb);
           } else {
             const int box_bytes = p.block_k * ROW_BYTES;
-            for (int j = 0; j < BLOCK_N / elems_per_row; j++)
-              tma_load_3d(&map_b, &full[stage], sb + j * box_bytes, n0 + j * elems_per_row, k0, bb);
+            for (int j = 0; j < C::B_ROWS / elems_per_row; j++)
+              load(&map_b, sb + j * box_bytes, n0 + j * elems_per_row, k0, bb);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (the leader CTA only when PAIR) =====
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -244,13 +351,17 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // K-major: 8-row groups 1024 B apart, a k-step is 32 B inside the swizzle row.
     // MN-major: atoms of 128 B x 8 k-rows, next MN atom one TMA box away, a k-step is
     // (32 / esize) k-rows = that many 128-byte rows.
-    const uint32_t a_lbo = p.a_mn ? box_bytes : 16, a_sbo = 1024;
-    const uint32_t b_lbo = p.b_mn ? box_bytes : 16, b_sbo = 1024;
+    // MN-major tf32: the 32-byte-atom swizzle repeats every 4 k-rows (512 B), not 8
+    const bool a32 = p.a_mn && p.esize == 4, b32 = p.b_mn && p.esize == 4;
+    const uint32_t a_lbo = p.a_mn ? box_bytes : 16, a_sbo = a32 ? 512 : 1024;
+    const uint32_t b_lbo = p.b_mn ? box_bytes : 16, b_sbo = b32 ? 512 : 1024;
+    const uint64_t a_lay = a32 ? 1 : 2, b_lay = b32 ? 1 : 2;
     const uint32_t kstep_rows = 32 / p.esize;
     const uint32_t a_kstep = p.a_mn ? kstep_rows * ROW_BYTES : 32;
     const uint32_t b_kstep = p.b_mn ? kstep_rows * ROW_BYTES : 32;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      mbar_wait(&tempty[as], aphase ^ 1);
+    for (int64_t t = worker; t < total_tiles; t += nworkers) {
+      if (PAIR) mbar_wait_cluster(&tempty[as], aphase ^ 1);
+      else mbar_wait(&tempty[as], aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)as * BLOCK_N;
       for (int kb = 0; kb < p.num_kb; kb++) {
@@ -261,38 +372,48 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const uint64_t ad = make_desc(sa + j * a_kstep, a_lbo, a_sbo);
-            const uint64_t bd = make_desc(sb + j * b_kstep, b_lbo, b_sbo);
+            const uint64_t ad = make_desc(sa + j * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t bd = make_desc(sb + j * b_kstep, b_lbo, b_sbo, b_lay);
             const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-            if (p.esize == 2) umma_f16(tmem_d, ad, bd, p.idesc, acc);
-            else umma_tf32(tmem_d, ad, bd, p.idesc, acc);
+            if (PAIR) {
+              if (p.esize == 2) umma_f16_pair(tmem_d, ad, bd, p.idesc, acc);
+              else umma_tf32_pair(tmem_d, ad, bd, p.idesc, acc);
+            } else {
+              if (p.esize == 2) umma_f16(tmem_d, ad, bd, p.idesc, acc);
+              else umma_tf32(tmem_d, ad, bd, p.idesc, acc);
+            }
           }
         }
         __syncwarp();
         if (elect_one()) {
-          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
+          if (PAIR) {  // both CTAs' producers / epilogues are released
+            umma_commit_pair(&empty[stage]);
+            if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as]);
+          } else {
+            umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+            if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (p.num_kb == 0) {  // k == 0: nothing accumulates; the epilogue writes zeros
-        if (elect_one()) umma_commit(&tfull[as]);
+        if (elect_one()) { if (PAIR) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]); }
         __syncwarp();
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     int as = 0;
     uint32_t aphase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int64_t t = worker; t < total_tiles; t += nworkers) {
       int bi, mb, nb;
       tile_coords(p, t, bi, mb, nb);
       mbar_wait(&tfull[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = (int64_t)mb * BLOCK_M + q * 32 + lane;
+      const int64_t row = (int64_t)mb * C::TILE_M + (int64_t)rank * BLOCK_M + q * 32 + lane;
       const int64_t col0 = (int64_t)nb * BLOCK_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BLOCK_N;
       const int64_t crow = (int64_t)bi * p.c_bs + row * p.c_rs;
@@ -340,16 +461,25 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(leader_addr(&tempty[as]));
+        else mbar_arrive(&tempty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  // PAIR: neither CTA may retire while the other can still read its smem or signal its barriers
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -360,7 +490,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 // Build the 3-D tensor map (inner, outer, batch) of one operand.
 bool encode_operand(nxc_ctx *ctx, CUtensorMap *map, const void *base, CUtensorMapDataType dt, int esize,
                     int64_t inner_extent, int64_t outer_extent, int64_t outer_stride_elems, int64_t nbatch,
-                    int64_t batch_stride_elems, int box_outer) {
+                    int64_t batch_stride_elems, int box_outer, bool atom32 = false) {
   EncodeTiledFn fn = (EncodeTiledFn)ctx->encode_tiled;
   if (!fn) return false;
   if (((uintptr_t)base & 15) != 0) return false;
@@ -373,7 +503,8 @@ bool encode_operand(nxc_ctx *ctx, CUtensorMap *map, const void *base, CUtensorMa
   cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / esize), (cuuint32_t)box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, dt, 3, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -404,12 +535,20 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
     b_b = b_bs != 0;
   }
 
+  // One 256x256 tile per CTA pair when M fills it; the single-CTA 128x256 kernel otherwise
+  // (M <= 128, or a 128-row remainder that would leave half of the pair idle too often).
+  const int64_t num_m128 = (q.m + BLOCK_M - 1) / BLOCK_M;
+  bool pair = num_m128 >= 2 && ((num_m128 & 1) == 0 || num_m128 >= 8);
+  if (const char *f = getenv("NX_CUDA_MM_PAIR")) pair = f[0] == '1';  // test / tuning override
+  const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
+  const int b_rows = pair ? BLOCK_N / 2 : BLOCK_N;
+
   TcParams p;
   p.m = q.m; p.n = q.n; p.k = q.k; p.nbatch = q.nbatch;
   p.c_rs = q.c_rs; p.c_bs = c_bs;
   p.esize = esize;
   p.block_k = ROW_BYTES / esize;
-  p.num_m = (int)((q.m + BLOCK_M - 1) / BLOCK_M);
+  p.num_m = (int)((q.m + tile_m - 1) / tile_m);
   p.num_n = (int)((q.n + BLOCK_N - 1) / BLOCK_N);
   p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
   p.a_batched = a_b; p.b_batched = b_b;
@@ -434,25 +573,48 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   CUtensorMap map_a, map_b;
   bool ok;
   if (!p.a_mn) ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.k, q.m, q.a_rs, a_b ? q.nbatch : 1, a_bs, BLOCK_M);
-  else ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.m, q.k, q.a_cs, a_b ? q.nbatch : 1, a_bs, p.block_k);
+  else ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.m, q.k, q.a_cs, a_b ? q.nbatch : 1, a_bs, p.block_k, esize == 4);
   if (!ok) return NXC_MM_TC_DECLINED;
-  if (!p.b_mn) ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.k, q.n, q.b_cs, b_b ? q.nbatch : 1, b_bs, BLOCK_N);
-  else ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.n, q.k, q.b_rs, b_b ? q.nbatch : 1, b_bs, p.block_k);
+  if (!p.b_mn) ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.k, q.n, q.b_cs, b_b ? q.nbatch : 1, b_bs, b_rows);
+  else ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.n, q.k, q.b_rs, b_b ? q.nbatch : 1, b_bs, p.block_k, esize == 4);
   if (!ok) return NXC_MM_TC_DECLINED;
 
-  // instruction descriptor: D = f32, A/B format, majors, N >> 3, M >> 4
+  // instruction descriptor: D = f32, A/B format, majors, N >> 3, M >> 4 (M = 256 across the pair)
   const uint32_t fmt = q.dt == NXC_BF16 ? 1u : q.dt == NXC_F16 ? 0u : 2u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
 
   static bool attr_set = false;
   if (!attr_set) {
-    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<false>::SMEM_BYTES));
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true>::SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
-  const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-  nxc_mm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
+  if (!pair) {
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    nxc_mm_tc_kernel<false><<<grid, NUM_THREADS, Cfg<false>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
+  } else {
+    const int64_t pairs = ctx->sm_count / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<true>::SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void *out = (void *)q.c;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, nxc_mm_tc_kernel<true>, map_a, map_b, out, p);
+    if (e != cudaSuccess) return nxc_cuda_fail(ctx, e, "cluster launch");
+  }
   NXC_LAUNCH_CHECK(ctx);
   return NXC_OK;
 }

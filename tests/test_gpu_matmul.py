@@ -118,3 +118,61 @@ def test_matmul_errors(ctx):
     # k == 0 is a real zero fill
     z = B.matmul(B.buffer(ctx, D.float32, [3, 0]), B.buffer(ctx, D.float32, [0, 2]))
     assert (H.download(z) == 0).all()
+
+
+@pytest.fixture
+def pair_mode(request):
+    """Force the tcgen05 GEMM's tile mode: "1" = 2-CTA pair (cta_group::2, 256x256 tiles),
+    "0" = single CTA (128x256). The env override is read at every launch."""
+    import os
+    old = os.environ.get("NX_CUDA_MM_PAIR")
+    os.environ["NX_CUDA_MM_PAIR"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["NX_CUDA_MM_PAIR"]
+    else:
+        os.environ["NX_CUDA_MM_PAIR"] = old
+
+
+TC_SHAPES = [(256, 256, 256), (512, 384, 640), (300, 4100, 200), (128, 64, 256), (1024, 1024, 1024),
+             (2048, 512, 1536), (257, 72, 264)]
+
+
+@pytest.mark.parametrize("pair_mode", ["0", "1"], indirect=True)
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "tf32"])
+def test_matmul_tc_tile_modes(ctx, oracle, dtype, pair_mode):
+    """Both tile modes of the tensor-core GEMM against the oracle: M/N/K tails (a pair whose
+    second CTA is entirely past M), all four operand majors, batched + batch-broadcast.
+    tf32 = f32 operands in the opt-in tf32 mode, 1e-3 relative (north_star)."""
+    st = "f32" if dtype == "tf32" else dtype
+    if dtype == "tf32":
+        ctx.set_matmul_mode("tf32")
+    try:
+        rng = np.random.default_rng(1)
+        for (m, k, n) in TC_SHAPES:
+            A = H.to_storage(st, rng.standard_normal((m, k)) / np.sqrt(k))
+            Bm = H.to_storage(st, rng.standard_normal((k, n)))
+            a = H.HostView(A.reshape(-1).copy(), st, [m, k])
+            b = H.HostView(Bm.reshape(-1).copy(), st, [k, n])
+            at = H.HostView(np.ascontiguousarray(A.T).reshape(-1), st, [k, m]).permute([1, 0])
+            bt = H.HostView(np.ascontiguousarray(Bm.T).reshape(-1), st, [n, k]).permute([1, 0])
+            for name, (x, y) in {"nn": (a, b), "tn": (at, b), "nt": (a, bt), "tt": (at, bt)}.items():
+                want = oracle.matmul(x, y).numpy()
+                got = H.download(B.matmul(H.upload(ctx, x), H.upload(ctx, y)))
+                wf, gf = H.storage_to_float(st, want), H.storage_to_float(st, got)
+                scale = float(np.max(np.abs(wf))) or 1.0
+                tol = 1e-3 if dtype == "tf32" else _tol(dtype, k)
+                err = float(np.max(np.abs(gf - wf)))
+                assert err <= tol * scale, f"{dtype}/pair={pair_mode}/{(m, k, n)}/{name}: err {err} scale {scale}"
+        # batched: [3, m, k] x [k, n] (broadcast rhs) and [3, m, k] x [3, k, n]
+        m, k, n = 384, 96, 320
+        A = H.to_storage(st, rng.standard_normal((3, m, k)) / np.sqrt(k))
+        Bm = H.to_storage(st, rng.standard_normal((3, k, n)))
+        a = H.HostView(A.reshape(-1).copy(), st, [3, m, k])
+        for b in (H.HostView(Bm[0].reshape(-1).copy(), st, [k, n]), H.HostView(Bm.reshape(-1).copy(), st, [3, k, n])):
+            want = H.storage_to_float(st, oracle.matmul(a, b).numpy())
+            got = H.storage_to_float(st, H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, b))))
+            tol = 1e-3 if dtype == "tf32" else _tol(dtype, k)
+            assert float(np.max(np.abs(got - want))) <= tol * (float(np.max(np.abs(want))) or 1.0), f"batched/{dtype}"
+    finally:
+        ctx.set_matmul_mode("f32")
