@@ -67,6 +67,7 @@ struct TcParams {
   int out_f32;            // C is f32 (tf32 mode) else 16-bit
   int out_bf16;           // 16-bit flavour
   int vec_store;          // rows of C are 16-byte aligned
+  int group;              // M-blocks per rasterisation group
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -241,7 +242,7 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int64_t t, int &b
   const int64_t per_batch = (int64_t)p.num_m * p.num_n;
   bi = (int)(t / per_batch);
   int r = (int)(t - (int64_t)bi * per_batch);
-  const int GROUP = 8;
+  const int GROUP = p.group;
   const int per_group = GROUP * p.num_n;
   const int g = r / per_group;
   const int first_m = g * GROUP;
@@ -552,6 +553,8 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.num_n = (int)((q.n + BLOCK_N - 1) / BLOCK_N);
   p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
   p.a_batched = a_b; p.b_batched = b_b;
+  p.group = 8;
+  if (const char *f = getenv("NX_CUDA_MM_GROUP")) p.group = atoi(f) > 0 ? atoi(f) : 8;
   p.out_f32 = (q.dt == NXC_F32);
   p.out_bf16 = (q.dt == NXC_BF16);
   p.vec_store = (((uintptr_t)q.c & 15) == 0) && ((q.c_rs * esize) % 16 == 0) && ((c_bs * esize) % 16 == 0);
