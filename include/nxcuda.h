@@ -20,7 +20,7 @@
  *     Invalid_argument when nxc_status_is_invalid_argument() says so, Failure
  *     otherwise (reference: nx_c_engine.c:1345-1351).
  *   - every launch is asynchronous on the context's stream; only nxc_sync and
- *     nxc_d2h block. There is no CPU fallback anywhere in this library.
+ *     nxc_d2h block (nxc_sync also drains the copy / communication side streams). There is no CPU fallback anywhere in this library.
  */
 #ifndef NXCUDA_H
 #define NXCUDA_H
@@ -115,6 +115,14 @@ NXC_API nxc_status nxc_host_free(nxc_ctx *ctx, void *hptr);
 NXC_API nxc_status nxc_h2d(nxc_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async */
 NXC_API nxc_status nxc_d2h(nxc_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* blocks */
 NXC_API nxc_status nxc_memset(nxc_ctx *ctx, void *dst_dev, int byte, size_t bytes);
+/* Copy engines. nxc_h2d from PINNED host memory (nxc_host_alloc) of >= 1 MiB runs on a dedicated
+   host->device stream, ordered after the work already queued and before the work queued later on
+   the context stream. nxc_d2h_async copies into PINNED host memory on a dedicated device->host
+   stream, ordered after the work already queued; it does not block and later kernels do not wait
+   for it, so step i's read-back overlaps step i+1's upload and compute. The data is in dst_host
+   after nxc_sync (which drains every stream of the context). nxc_free of src_dev may be called
+   at once: the engine defers the release until the copy has finished. */
+NXC_API nxc_status nxc_d2h_async(nxc_ctx *ctx, void *dst_host_pinned, const void *src_dev, size_t bytes);
 
 /* ---- map family -----------------------------------------------------------
    replaces caml_nx_c_{neg..erf}, caml_nx_c_{add..shr}, caml_nx_c_cmp*,
@@ -196,6 +204,12 @@ NXC_API nxc_status nxc_dist_finalize(nxc_ctx *ctx);
 NXC_API nxc_status nxc_allreduce(nxc_ctx *ctx, void *dev_buf, int64_t count, int dtype, int op);
 NXC_API nxc_status nxc_allgather(nxc_ctx *ctx, const void *dev_send, void *dev_recv,
                          int64_t bytes_per_rank);
+/* The same allreduce on the context's communication stream: ordered after the work already
+   queued, but kernels queued later do NOT wait for it (a gradient bucket reduces under the rest
+   of the backward pass). nxc_comm_wait makes everything queued afterwards wait for all async
+   collectives issued so far (no host block). The buffer must stay allocated until then. */
+NXC_API nxc_status nxc_allreduce_async(nxc_ctx *ctx, void *dev_buf, int64_t count, int dtype, int op);
+NXC_API nxc_status nxc_comm_wait(nxc_ctx *ctx);
 
 #ifdef __cplusplus
 }

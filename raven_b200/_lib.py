@@ -57,6 +57,7 @@ SYMBOLS = {
     "nxc_host_free": (_S, [_P, _P]),
     "nxc_h2d": (_S, [_P, _P, _P, ctypes.c_size_t]),
     "nxc_d2h": (_S, [_P, _P, _P, ctypes.c_size_t]),
+    "nxc_d2h_async": (_S, [_P, _P, _P, ctypes.c_size_t]),
     "nxc_memset": (_S, [_P, _P, ctypes.c_int, ctypes.c_size_t]),
     "nxc_map1": (_S, [_P, ctypes.c_int, _T, _T]),
     "nxc_map2": (_S, [_P, ctypes.c_int, _T, _T, _T]),
@@ -81,6 +82,8 @@ SYMBOLS = {
     "nxc_dist_init": (_S, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "nxc_dist_finalize": (_S, [_P]),
     "nxc_allreduce": (_S, [_P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "nxc_allreduce_async": (_S, [_P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "nxc_comm_wait": (_S, [_P]),
     "nxc_allgather": (_S, [_P, _P, _P, ctypes.c_int64]),
 }
 

@@ -62,6 +62,20 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.nxc_launch_count(self._p))
 
+    def pinned_empty(self, n: int, dtype) -> np.ndarray:
+        """A 1-D numpy array over page-locked host memory (nxc_host_alloc). `from_host` of such an
+        array goes through the upload engine and `to_host_async` writes into one; the memory
+        lives as long as the array (or any view of it) does."""
+        npdt = np.dtype(dtype)
+        p = ctypes.c_void_p()
+        check(self._p, "host_alloc", self._lib.nxc_host_alloc(self._p, _b.max(n * npdt.itemsize, 1), ctypes.byref(p)))
+        raw = (ctypes.c_uint8 * _b.max(n * npdt.itemsize, 1)).from_address(p.value)
+        arr = np.frombuffer(raw, dtype=npdt, count=n)
+        lib, ctxp = self._lib, self._p
+        import weakref
+        weakref.finalize(raw, lambda: lib.nxc_host_free(ctxp, p))
+        return arr
+
     def stream(self) -> int:
         return int(self._lib.nxc_stream(self._p) or 0)
 
@@ -161,6 +175,18 @@ def to_host(t: Tensor) -> np.ndarray:
         check(t.context.ptr, "to_host",
               t.context._lib.nxc_d2h(t.context.ptr, host.ctypes.data, t.buffer.ptr, host.nbytes))
     return host
+
+
+def to_host_async(t: Tensor, pinned_out: np.ndarray) -> None:
+    """Start copying the STORAGE of `t` into `pinned_out` (from Context.pinned_empty) on the
+    download engine and return at once: later kernels do not wait for it and the next step's
+    uploads overlap it. The data is valid after `ctx.sync()`. `t` may be dropped right away."""
+    n = t.buffer.nbytes
+    if pinned_out.nbytes < n:
+        raise InvalidArgument("to_host_async: destination smaller than the tensor's storage")
+    if n:
+        check(t.context.ptr, "to_host_async",
+              t.context._lib.nxc_d2h_async(t.context.ptr, pinned_out.ctypes.data, t.buffer.ptr, n))
 
 
 def to_numpy(t: Tensor) -> np.ndarray:

@@ -57,7 +57,16 @@ struct nxc_ctx {
   int rank, world;
   // TMA descriptor encoder (driver entry point fetched at runtime)
   void *encode_tiled;
+  // Side streams (created on first use): pinned host->device and device->host copies run on
+  // their own streams so the two PCIe directions and the compute stream overlap; collectives
+  // issued through nxc_allreduce_async run on comm_stream under the following kernels.
+  cudaStream_t h2d_stream, d2h_stream, comm_stream;
+  cudaEvent_t ev_fork, ev_h2d, ev_comm;  // reusable ordering events
+  // device buffers with an nxc_d2h_async still reading them: their free is deferred
+  struct nxc_pending { void *ptr; cudaEvent_t done; int freed; } *pending;
+  int n_pending, cap_pending;
 };
+nxc_status nxc_side_streams(nxc_ctx *ctx);
 
 nxc_status nxc_cuda_fail(nxc_ctx *ctx, cudaError_t e, const char *what);
 nxc_status nxc_scratch(nxc_ctx *ctx, size_t bytes, void **out);

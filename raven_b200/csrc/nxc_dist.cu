@@ -88,6 +88,7 @@ extern "C" nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const voi
 extern "C" nxc_status nxc_dist_finalize(nxc_ctx *ctx) {
   if (ctx->nccl_comm) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = NULL;
   }
@@ -110,7 +111,25 @@ static int nccl_dtype(int dt) {
   }
 }
 
+static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op, cudaStream_t stream);
+
 extern "C" nxc_status nxc_allreduce(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+  return allreduce_on(ctx, buf, count, dtype, op, ctx->stream);
+}
+extern "C" nxc_status nxc_allreduce_async(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+  nxc_status s = nxc_side_streams(ctx);
+  if (s) return s;
+  NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  NXC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+  return allreduce_on(ctx, buf, count, dtype, op, ctx->comm_stream);
+}
+extern "C" nxc_status nxc_comm_wait(nxc_ctx *ctx) {
+  if (!ctx->comm_stream) return NXC_OK;
+  NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  NXC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+  return NXC_OK;
+}
+static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op, cudaStream_t stream) {
   if (!ctx->nccl_comm) { snprintf(ctx->err, sizeof ctx->err, "%s: nxc_dist_init not called", NXC_ERR_NCCL); return NXC_ERR_NCCL; }
   int nd = nccl_dtype(dtype);
   int64_t n = count;
@@ -118,7 +137,7 @@ extern "C" nxc_status nxc_allreduce(nxc_ctx *ctx, void *buf, int64_t count, int 
   if (dtype == NXC_C32 && op == NXC_SUM) { nd = ncclFloat32; n = 2 * count; }
   if (dtype == NXC_C64 && op == NXC_SUM) { nd = ncclFloat64; n = 2 * count; }
   if (nd < 0 || op < 0 || op > NXC_RMIN) return NXC_ERR_UNSUPPORTED_DTYPE;
-  ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)n, nd, op, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)n, nd, op, (ncclComm_t)ctx->nccl_comm, stream);
   if (r) return nccl_fail(ctx, r, "ncclAllReduce");
   ctx->launches++;
   return NXC_OK;

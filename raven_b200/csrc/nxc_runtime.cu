@@ -83,10 +83,51 @@ extern "C" nxc_status nxc_ctx_create(nxc_ctx **out) {
   return nxc_ctx_create_on(dev, NULL, out);
 }
 
+// ---- side streams and deferred frees ----------------------------------------------------------
+nxc_status nxc_side_streams(nxc_ctx *ctx) {
+  if (ctx->h2d_stream) return NXC_OK;
+  NXC_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  NXC_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  NXC_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  NXC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  NXC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+  NXC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  return NXC_OK;
+}
+// Release the buffers whose read-back has finished (`drain`: wait for the rest first).
+static void nxc_reap_pending(nxc_ctx *ctx, bool drain) {
+  int w = 0;
+  for (int i = 0; i < ctx->n_pending; i++) {
+    nxc_ctx::nxc_pending &e = ctx->pending[i];
+    bool done = drain ? (cudaEventSynchronize(e.done) == cudaSuccess, true) : (cudaEventQuery(e.done) == cudaSuccess);
+    if (done) {
+      if (e.freed) cudaFreeAsync(e.ptr, ctx->stream);
+      cudaEventDestroy(e.done);
+    } else {
+      ctx->pending[w++] = e;
+    }
+  }
+  ctx->n_pending = w;
+  cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+}
+
 extern "C" void nxc_ctx_destroy(nxc_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->h2d_stream) {
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamSynchronize(ctx->comm_stream);
+    nxc_reap_pending(ctx, true);
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_h2d);
+    cudaEventDestroy(ctx->ev_comm);
+  }
+  free(ctx->pending);
   if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
@@ -94,6 +135,12 @@ extern "C" void nxc_ctx_destroy(nxc_ctx *ctx) {
 
 extern "C" nxc_status nxc_sync(nxc_ctx *ctx) {
   NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h2d_stream) {
+    NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->h2d_stream));
+    NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    nxc_reap_pending(ctx, true);
+  }
   return NXC_OK;
 }
 extern "C" void *nxc_stream(nxc_ctx *ctx) { return (void *)ctx->stream; }
@@ -131,11 +178,20 @@ extern "C" int64_t nxc_elem_size(int dt) {
 extern "C" nxc_status nxc_alloc(nxc_ctx *ctx, size_t bytes, void **dptr) {
   *dptr = NULL;
   if (bytes == 0) bytes = 16;
+  if (ctx->n_pending) nxc_reap_pending(ctx, false);
   NXC_CUDA_TRY(ctx, cudaMallocAsync(dptr, bytes, ctx->stream));
   return NXC_OK;
 }
 extern "C" nxc_status nxc_free(nxc_ctx *ctx, void *dptr) {
   if (!dptr) return NXC_OK;
+  if (ctx->n_pending) {
+    nxc_reap_pending(ctx, false);
+    for (int i = 0; i < ctx->n_pending; i++)
+      if (ctx->pending[i].ptr == dptr) {  // a read-back still owns it: released by nxc_reap_pending
+        ctx->pending[i].freed = 1;
+        return NXC_OK;
+      }
+  }
   NXC_CUDA_TRY(ctx, cudaFreeAsync(dptr, ctx->stream));
   return NXC_OK;
 }
@@ -148,9 +204,51 @@ extern "C" nxc_status nxc_host_free(nxc_ctx *ctx, void *hptr) {
   if (hptr) NXC_CUDA_TRY(ctx, cudaFreeHost(hptr));
   return NXC_OK;
 }
+static bool nxc_is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
 extern "C" nxc_status nxc_h2d(nxc_ctx *ctx, void *dst, const void *src, size_t bytes) {
   if (bytes == 0) return NXC_OK;
+  if (bytes >= ((size_t)1 << 20) && nxc_is_pinned(src)) {
+    // upload engine: after what is queued (dst's allocation included), before what follows
+    nxc_status s = nxc_side_streams(ctx);
+    if (s) return s;
+    NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    NXC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_fork, 0));
+    NXC_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_h2d, ctx->h2d_stream));
+    NXC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
+    return NXC_OK;
+  }
   NXC_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NXC_OK;
+}
+extern "C" nxc_status nxc_d2h_async(nxc_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return NXC_OK;
+  if (!nxc_is_pinned(dst)) {
+    snprintf(ctx->err, sizeof ctx->err, "%s: nxc_d2h_async needs pinned host memory (nxc_host_alloc)", NXC_ERR_CUDA);
+    return NXC_ERR_CUDA;
+  }
+  nxc_status s = nxc_side_streams(ctx);
+  if (s) return s;
+  NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  NXC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_fork, 0));
+  NXC_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  if (ctx->n_pending == ctx->cap_pending) {
+    int cap = ctx->cap_pending ? 2 * ctx->cap_pending : 8;
+    void *np = realloc(ctx->pending, cap * sizeof *ctx->pending);
+    if (!np) return NXC_ERR_ALLOC;
+    ctx->pending = (nxc_ctx::nxc_pending *)np;
+    ctx->cap_pending = cap;
+  }
+  nxc_ctx::nxc_pending &e = ctx->pending[ctx->n_pending];
+  e.ptr = (void *)src;
+  e.freed = 0;
+  NXC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming));
+  NXC_CUDA_TRY(ctx, cudaEventRecord(e.done, ctx->d2h_stream));
+  ctx->n_pending++;
   return NXC_OK;
 }
 extern "C" nxc_status nxc_d2h(nxc_ctx *ctx, void *dst, const void *src, size_t bytes) {

@@ -63,6 +63,22 @@ class NcclComm:
               self.ctx._lib.nxc_allreduce(self.ctx.ptr, t.buffer.ptr, n, t.dtype.tag, _OPS[op]))
         return t
 
+    def allreduce_async(self, t: B.Tensor, op: str) -> B.Tensor:
+        """In place on the communication stream: ordered after the kernels already queued, NOT
+        waited for by the ones queued next (a gradient bucket reduces under the rest of the
+        backward pass). Call `wait()` before anything reads `t`."""
+        assert B.is_c_contiguous(t)
+        n = 1
+        for s in t.shape:
+            n *= s
+        check(self.ctx.ptr, "allreduce",
+              self.ctx._lib.nxc_allreduce_async(self.ctx.ptr, t.buffer.ptr, n, t.dtype.tag, _OPS[op]))
+        return t
+
+    def wait(self) -> None:
+        """Everything queued after this waits for the async collectives issued so far."""
+        check(self.ctx.ptr, "comm_wait", self.ctx._lib.nxc_comm_wait(self.ctx.ptr))
+
     def allgather(self, t: B.Tensor) -> B.Tensor:
         """[world, *t.shape], rank-major."""
         t = B.contiguous(t)
@@ -130,6 +146,36 @@ def sharded_batch_matmul(a_local, b_local, comm=None, gather: bool = False, back
         shp = tuple(g.shape)
         return backend.reshape(g, (shp[0] * shp[1],) + shp[2:])
     return c
+
+
+class GradBucketReducer:
+    """Data-parallel gradient averaging overlapped with the backward pass: `push(leaf)` as each
+    gradient leaf is produced starts its sum-allreduce on the communication stream (NCCL over
+    NVLink) while the following backward kernels run; `finish()` makes the stream wait for the
+    exchanges and returns the leaves scaled by 1/world, in push order. Same answer as
+    `allreduce_mean_`, which reduces after the backward pass."""
+
+    def __init__(self, comm, backend=B):
+        self.comm, self.backend, self.leaves = comm, backend, []
+
+    def push(self, t):
+        t = self.backend.contiguous(t)
+        if hasattr(self.comm, "allreduce_async"):
+            self.comm.allreduce_async(t, "sum")
+        else:
+            t = self.comm.allreduce(t, "sum")
+        self.leaves.append(t)
+        return t
+
+    def finish(self):
+        if hasattr(self.comm, "wait"):
+            self.comm.wait()
+        out, be = [], self.backend
+        for t in self.leaves:
+            inv = be.full(t.context, t.dtype, [], 1.0 / self.comm.world)
+            out.append(be.mul(t, be.expand(inv, t.shape) if len(t.shape) else inv))
+        self.leaves = []
+        return out
 
 
 def allreduce_mean_(tensors, comm, backend=B):

@@ -140,6 +140,14 @@ def _worker(rank, world, port, q):
         g = OT(HostView(np.full(8, float(rank + 1), np.float32), "f32", [8]))
         avg = sharded.allreduce_mean_([g], comm, backend=be)[0].hv.numpy()
         assert np.allclose(avg, 1.5)
+        # the bucketed reducer (async on NCCL, synchronous on this double) gives the same leaves
+        red = sharded.GradBucketReducer(comm, backend=be)
+        for k in range(3):
+            red.push(OT(HostView(np.full(4 + k, float((rank + 1) * (k + 1)), np.float32), "f32", [4 + k])))
+        outs = red.finish()
+        assert [tuple(t.hv.shape) for t in outs] == [(4,), (5,), (6,)]
+        for k, t in enumerate(outs):
+            assert np.allclose(t.hv.numpy(), 1.5 * (k + 1))
         td.barrier()
         td.destroy_process_group()
         q.put((rank, "ok"))

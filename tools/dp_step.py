@@ -63,7 +63,10 @@ two_inv = B.mul(inv, B.full(ctx, dt, [], 2.0))
 lr = B.full(ctx, dt, [], 1e-3)
 
 
-def grads():
+OVERLAP = os.environ.get("DP_OVERLAP", "1") == "1"
+
+
+def grads(reducer=None):
     hs, pres, h = [x], [], x
     for W, b in zip(Ws, bs):
         pre = B.add(B.matmul(h, W), B.expand(B.reshape(b, [1, WIDTH]), [BATCH, WIDTH]))
@@ -76,7 +79,10 @@ def grads():
     out = []
     for li in range(LAYERS - 1, -1, -1):
         g = B.mul(g, B.cast(B.cmplt(B.expand(zero, [BATCH, WIDTH]), pres[li]), dt))
-        out.append((li, B.matmul(B.permute(hs[li], [1, 0]), g), B.reduce(g, "sum", [0])))
+        dW, db = B.matmul(B.permute(hs[li], [1, 0]), g), B.reduce(g, "sum", [0])
+        if reducer is not None:   # the bucket's exchange runs under the next layer's backward GEMMs
+            dW, db = reducer.push(dW), reducer.push(db)
+        out.append((li, dW, db))
         if li > 0:
             g = B.matmul(g, B.permute(Ws[li], [1, 0]))
     return loss, out
@@ -88,11 +94,14 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 def step(timed=False):
     if timed:
         ev[0].record(stream)
-    loss, gs = grads()
+    reducer = sharded.GradBucketReducer(comm) if (comm is not None and OVERLAP) else None
+    loss, gs = grads(reducer)
     if timed:
         ev[1].record(stream)
     leaves = [t for _, dW, db in gs for t in (dW, db)]
-    if comm is not None:
+    if reducer is not None:
+        leaves = reducer.finish()
+    elif comm is not None:
         leaves = sharded.allreduce_mean_(leaves, comm)
     if timed:
         ev[2].record(stream)
@@ -128,7 +137,8 @@ if rank == 0:
                                   f"of {nparams} params ({nparams * dt.itemsize / 1e6:.0f} MB) + SGD",
                       "n_gpus": world, "ms_per_step": round(ms, 3), "samples_per_s": round(world * BATCH / (ms * 1e-3), 1),
                       "grad_ms": round(comp / reps, 3), "exchange_ms": round(exch / reps, 3),
-                      "scaling": "weak"}))
+                      "exchange": "bucketed allreduce on the comm stream under the backward pass" if OVERLAP
+                      else "allreduce after the backward pass", "scaling": "weak"}))
 if comm is not None:
     ctx.sync()
     comm.close()
