@@ -365,8 +365,8 @@ def main():
         b = B.from_host(ctx, pb)
         A = B.reshape(a, [rows_local, side])
         r0, r1, r2, s0, s1, s2, am = step()
-        B.to_host_async(r0, pr)
-        got = [B.to_host(x) for x in (s0, s1, s2, am)]
+        got = [B.to_host(x) for x in (s0, s1, s2, am)]   # small, blocking: first, so they do not
+        B.to_host_async(r0, pr)                            # queue behind the 1 GiB read-back
         return got
 
     e2e_steps = max(2, min(args.steps, 5))

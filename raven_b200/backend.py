@@ -51,6 +51,7 @@ class Context:
         check(None, "create_context", st)
         self._p = p
         self._lib = lib
+        self._pinned = []   # [lo, hi) address ranges handed out by pinned_empty
 
     @property
     def ptr(self):
@@ -69,12 +70,21 @@ class Context:
         npdt = np.dtype(dtype)
         p = ctypes.c_void_p()
         check(self._p, "host_alloc", self._lib.nxc_host_alloc(self._p, _b.max(n * npdt.itemsize, 1), ctypes.byref(p)))
-        raw = (ctypes.c_uint8 * _b.max(n * npdt.itemsize, 1)).from_address(p.value)
+        nbytes = _b.max(n * npdt.itemsize, 1)
+        raw = (ctypes.c_uint8 * nbytes).from_address(p.value)
         arr = np.frombuffer(raw, dtype=npdt, count=n)
-        lib, ctxp = self._lib, self._p
+        lib, ctxp, ranges, key = self._lib, self._p, self._pinned, (p.value, p.value + nbytes)
+        ranges.append(key)
         import weakref
-        weakref.finalize(raw, lambda: lib.nxc_host_free(ctxp, p))
+
+        def _release():
+            ranges.remove(key)
+            lib.nxc_host_free(ctxp, p)
+        weakref.finalize(raw, _release)
         return arr
+
+    def is_pinned(self, address: int) -> bool:
+        return any(lo <= address < hi for lo, hi in self._pinned)
 
     def stream(self) -> int:
         return int(self._lib.nxc_stream(self._p) or 0)
@@ -99,7 +109,7 @@ def create_context(device=None, stream=None) -> Context:
 class _Buffer:
     """A device allocation, shared by every handle viewing it."""
 
-    __slots__ = ("ctx", "ptr", "nbytes", "owned", "__weakref__")
+    __slots__ = ("ctx", "ptr", "nbytes", "owned", "_host_src", "__weakref__")
 
     def __init__(self, ctx: Context, nbytes: int, ptr=None):
         self.ctx = ctx
@@ -249,7 +259,12 @@ def from_host(ctx: Context, array: np.ndarray, dt=None) -> Tensor:
     t = _create(ctx, dt, (n,))
     if a.nbytes:
         check(ctx.ptr, "from_host", ctx._lib.nxc_h2d(ctx.ptr, t.buffer.ptr, a.ctypes.data, a.nbytes))
-        ctx.sync()  # the host array may be pageable / freed by the caller
+        if ctx.is_pinned(a.ctypes.data):
+            # page-locked source (Context.pinned_empty): the upload engine reads it asynchronously.
+            # The tensor keeps the array alive; the caller must not rewrite it before ctx.sync().
+            t.buffer._host_src = a
+        else:
+            ctx.sync()  # the host array may be freed or rewritten by the caller right away
     return t
 
 
