@@ -155,6 +155,23 @@ NXC_API nxc_status nxc_argreduce(nxc_ctx *ctx, int is_max, const nxc_tensor *out
 /* replaces caml_nx_c_cum{sum,prod,max,min} (reference: nx_c_fold.c:834-837). */
 NXC_API nxc_status nxc_scan(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *in, int axis);
 
+/* ---- fft family ------------------------------------------------------------
+   replaces caml_nx_c_fft / caml_nx_c_ifft / caml_nx_c_rfft / caml_nx_c_irfft
+   (reference: nx_c_fft.c:1173-1223; drivers :940-1143). UNNORMALISED transforms
+   (fft = -sign DFT, ifft = +sign DFT without 1/n), double-precision arithmetic for
+   both c32 and c64, any length. `out` is allocated by the binding: the input's
+   shape for fft/ifft; last transformed axis n/2+1 for rfft; `s_last` (or
+   2*(half-1) when s_last <= 0) for irfft, which truncates or zero-pads the
+   half-spectrum. Axis out of range / shape mismatch are Invalid_argument;
+   a non-complex (fft, irfft input) or non-real (rfft input) dtype is
+   Failure "unsupported bigarray kind". */
+NXC_API nxc_status nxc_fft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes,
+                           int n_axes, int inverse);
+NXC_API nxc_status nxc_rfft(nxc_ctx *ctx, const nxc_tensor *out_complex, const nxc_tensor *in_real,
+                            const int *axes, int n_axes);
+NXC_API nxc_status nxc_irfft(nxc_ctx *ctx, const nxc_tensor *out_real, const nxc_tensor *in_complex,
+                             const int *axes, int n_axes, int64_t s_last);
+
 /* ---- matmul ---------------------------------------------------------------
    replaces caml_nx_c_matmul (reference: nx_c_matmul.c:874-1108, 1271-1277).
    A [...,m,k] and B [...,k,n] at arbitrary strides with broadcast batch dims;
@@ -200,6 +217,12 @@ NXC_API nxc_status nxc_fold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tenso
 NXC_API nxc_status nxc_dist_unique_id(void *id_out_128);
 NXC_API nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const void *id_128);
 NXC_API nxc_status nxc_dist_finalize(nxc_ctx *ctx);
+/* 1 when nxc_dist_init mapped every peer's mailbox (CUDA IPC over NVLink): nxc_allreduce /
+   nxc_allgather of payloads up to 256 KiB per rank then run as ONE kernel that stores into the
+   peers' memory and waits on flags (allreduce folds the gathered partials in rank order with
+   the backend's own reduce, so every rank holds bit-identical results); larger payloads, the
+   async entry point and NX_CUDA_P2P=0 use NCCL. */
+NXC_API int nxc_dist_p2p_enabled(nxc_ctx *ctx);
 /* In-place allreduce over `count` elements of `dtype`; op is an nxc_reduce_op. */
 NXC_API nxc_status nxc_allreduce(nxc_ctx *ctx, void *dev_buf, int64_t count, int dtype, int op);
 NXC_API nxc_status nxc_allgather(nxc_ctx *ctx, const void *dev_send, void *dev_recv,

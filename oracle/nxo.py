@@ -229,3 +229,79 @@ def argsort(x, axis, descending=False):
     out = HostView.empty("i32", x.shape)
     _chk("argsort", lib().nxo_sort(1, ctypes.byref(_d(out)), ctypes.byref(_d(x)), int(axis), 1 if descending else 0))
     return out
+
+
+# ---- fft family -----------------------------------------------------------------------------
+# Restated from the DEFINITION the reference pins (nx_c_fft.c:38-41, 940-1143), not from its
+# mixed-radix algorithm: an unnormalised direct DFT in double precision, X[k] = sum_j x[j] *
+# exp(sign*2*pi*i*(j*k mod n)/n), one axis at a time in the reference's pass order, rounding to the
+# output type after every pass exactly where the reference stores (fft/rfft write `out` per axis;
+# irfft keeps a c64 temporary for the non-last axes). O(n^2): small cases only.
+def _dft_matrix(n, sign):
+    jk = (np.arange(n, dtype=np.int64)[:, None] * np.arange(n, dtype=np.int64)[None, :]) % max(n, 1)
+    ang = 2.0 * jk.astype(np.float64) / max(n, 1)
+    return np.cos(np.pi * ang) + 1j * sign * np.sin(np.pi * ang)
+
+
+def _dft_axis(a, axis, sign):
+    n = a.shape[axis]
+    if n == 0:
+        return a
+    w = _dft_matrix(n, sign)
+    return np.moveaxis(np.tensordot(w, np.moveaxis(a, axis, 0), axes=(1, 0)), 0, axis)
+
+
+def _cplx(dtype):
+    if dtype not in ("c32", "c64"):
+        raise RefError("Failure", "unsupported bigarray kind")
+    return np.complex64 if dtype == "c32" else np.complex128
+
+
+def _real(dtype):
+    if dtype not in ("f32", "f64"):
+        raise RefError("Failure", "unsupported bigarray kind")
+    return np.float32 if dtype == "f32" else np.float64
+
+
+def fft(x, axes, inverse=False):
+    ct = _cplx(x.dtype)
+    a = x.numpy()
+    for ax in axes:
+        if ax < 0 or ax >= a.ndim:
+            raise RefError("Invalid_argument", "axis out of range")
+        a = _dft_axis(a.astype(np.complex128), int(ax), 1 if inverse else -1).astype(ct)
+    return HostView.from_array(a, x.dtype)
+
+
+def rfft(x, dtype, axes):
+    _real(x.dtype)
+    ct = _cplx(dtype)
+    axes = [int(v) for v in axes]
+    a = x.numpy().astype(np.complex128)
+    last = axes[-1]
+    half = a.shape[last] // 2 + 1
+    a = np.take(_dft_axis(a, last, -1), np.arange(half), axis=last).astype(ct)
+    for ax in axes[:-1]:
+        a = _dft_axis(a.astype(np.complex128), ax, -1).astype(ct)
+    return HostView.from_array(a, dtype)
+
+
+def irfft(x, dtype, axes, s=None):
+    _cplx(x.dtype)
+    rt = _real(dtype)
+    axes = [int(v) for v in axes]
+    a = x.numpy().astype(np.complex128)
+    for ax in axes[:-1]:
+        a = _dft_axis(a, ax, 1)
+    last = axes[-1]
+    in_half = a.shape[last]
+    size = int(s[-1]) if s is not None else 2 * (in_half - 1)
+    half = min(in_half, size // 2 + 1)
+    g = np.moveaxis(a, last, -1)
+    f = np.zeros(g.shape[:-1] + (size,), dtype=np.complex128)
+    f[..., :half] = g[..., :half]
+    for k in range(1, half):
+        if size - k != k:
+            f[..., size - k] = np.conj(g[..., k])
+    out = _dft_axis(f, f.ndim - 1, 1).real.astype(rt)
+    return HostView.from_array(np.moveaxis(out, -1, last), dtype)

@@ -285,4 +285,29 @@ def argsort(x, axis, descending=False) -> HostView:
     return out
 
 
+# fft family: the binding owns the output shape (reference: backend_c/nx_backend.ml:520-549)
+def fft(x, axes, inverse=False) -> HostView:
+    out = HostView.empty(x.dtype, x.shape)
+    call("ifft" if inverse else "fft", out, x, [int(a) for a in axes])
+    return out
+
+
+def rfft(x, dtype, axes) -> HostView:
+    axes = [int(a) for a in axes]
+    shape = list(x.shape)
+    shape[axes[-1]] = shape[axes[-1]] // 2 + 1
+    out = HostView.empty(dtype, shape)
+    call("rfft", out, x, axes)
+    return out
+
+
+def irfft(x, dtype, axes, s=None) -> HostView:
+    axes = [int(a) for a in axes]
+    shape = list(x.shape)
+    shape[axes[-1]] = int(s[-1]) if s is not None else (shape[axes[-1]] - 1) * 2
+    out = HostView.empty(dtype, shape)
+    call("irfft", out, x, axes, [int(v) for v in s] if s is not None else [])
+    return out
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -232,12 +232,42 @@ let matmul x y =
   caml_matmul out x y;
   out
 
+(* ---- fft family (backend_c/nx_backend.ml:502-549): unnormalised; the binding owns the
+   output shape, the engine reads only the last entry of [s] ---- *)
+external caml_fft : bool -> (Complex.t, 'b) t -> (Complex.t, 'b) t -> int array -> unit = "nx_cuda_fft"
+external caml_rfft : (Complex.t, 'b) t -> (float, 'a) t -> int array -> unit = "nx_cuda_rfft"
+external caml_irfft : (float, 'b) t -> (Complex.t, 'a) t -> int array -> int array -> unit = "nx_cuda_irfft"
+
+let fft x ~axes =
+  let out = create_tensor x.context x.dtype x.shape in
+  caml_fft false out x axes;
+  out
+
+let ifft x ~axes =
+  let out = create_tensor x.context x.dtype x.shape in
+  caml_fft true out x axes;
+  out
+
+let rfft x ~dtype ~axes =
+  let last = axes.(Array.length axes - 1) in
+  let out_shape = Array.copy x.shape in
+  out_shape.(last) <- (x.shape.(last) / 2) + 1;
+  let out = create_tensor x.context dtype out_shape in
+  caml_rfft out x axes;
+  out
+
+let irfft ?s x ~dtype ~axes =
+  let last_idx = Array.length axes - 1 in
+  let last = axes.(last_idx) in
+  let size = match s with Some sizes -> sizes.(last_idx) | None -> (x.shape.(last) - 1) * 2 in
+  let out_shape = Array.copy x.shape in
+  out_shape.(last) <- size;
+  let out = create_tensor x.context dtype out_shape in
+  caml_irfft out x axes (match s with Some sizes -> sizes | None -> [||]);
+  out
+
 (* ---- not yet behind the C ABI (scope table 8f rank 4): fail loudly, never fall back ---- *)
 let todo op = failwith (op ^ ": not implemented by nx-cuda")
-let fft _ ~axes:_ = todo "fft"
-let ifft _ ~axes:_ = todo "ifft"
-let rfft _ ~dtype:_ ~axes:_ = todo "rfft"
-let irfft ?s:_ _ ~dtype:_ ~axes:_ = todo "irfft"
 let cholesky ~upper:_ _ = todo "cholesky"
 let triangular_solve ~upper:_ ~transpose:_ ~unit_diag:_ _ _ = todo "triangular_solve"
 let qr ~reduced:_ _ = todo "qr"

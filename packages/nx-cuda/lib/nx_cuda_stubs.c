@@ -273,3 +273,37 @@ CAMLprim value nx_cuda_sort(value varg, value vout, value vin, value vaxis, valu
   if (s) raise_status(Bool_val(varg) ? "argsort" : "sort", CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
+
+/* ---- fft family (replaces caml_nx_c_fft / _ifft / _rfft / _irfft, nx_c_fft.c:1173-1223) ---- */
+static int axes_of_value(value vaxes, int *axes) {
+  int n = (int)Wosize_val(vaxes);
+  if (n > NXC_MAX_NDIM) n = NXC_MAX_NDIM;
+  for (int i = 0; i < n; i++) axes[i] = Int_val(Field(vaxes, i));
+  return n;
+}
+CAMLprim value nx_cuda_fft(value vinv, value vout, value vin, value vaxes) {
+  CAMLparam4(vinv, vout, vin, vaxes);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int axes[NXC_MAX_NDIM], n = axes_of_value(vaxes, axes);
+  nxc_status s = nxc_fft(CTX_OF(vout), &o, &a, axes, n, Bool_val(vinv));
+  if (s) raise_status(Bool_val(vinv) ? "ifft" : "fft", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_rfft(value vout, value vin, value vaxes) {
+  CAMLparam3(vout, vin, vaxes);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int axes[NXC_MAX_NDIM], n = axes_of_value(vaxes, axes);
+  nxc_status s = nxc_rfft(CTX_OF(vout), &o, &a, axes, n);
+  if (s) raise_status("rfft", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_irfft(value vout, value vin, value vaxes, value vs) {
+  CAMLparam4(vout, vin, vaxes, vs);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  int axes[NXC_MAX_NDIM], n = axes_of_value(vaxes, axes);
+  int ns = (int)Wosize_val(vs);
+  int64_t s_last = ns > 0 ? Long_val(Field(vs, ns - 1)) : 0;
+  nxc_status s = nxc_irfft(CTX_OF(vout), &o, &a, axes, n, s_last);
+  if (s) raise_status("irfft", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}

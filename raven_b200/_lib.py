@@ -70,6 +70,9 @@ SYMBOLS = {
     "nxc_argreduce": (_S, [_P, ctypes.c_int, _T, _T, ctypes.c_int]),
     "nxc_scan": (_S, [_P, ctypes.c_int, _T, _T, ctypes.c_int]),
     "nxc_matmul": (_S, [_P, _T, _T, _T]),
+    "nxc_fft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
+    "nxc_rfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "nxc_irfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int64]),
     "nxc_pad": (_S, [_P, _T, _T, _P, ctypes.POINTER(ctypes.c_int64)]),
     "nxc_cat": (_S, [_P, _T, ctypes.POINTER(_T), ctypes.c_int, ctypes.c_int]),
     "nxc_gather": (_S, [_P, _T, _T, _T, ctypes.c_int]),
@@ -81,6 +84,7 @@ SYMBOLS = {
     "nxc_dist_unique_id": (_S, [_P]),
     "nxc_dist_init": (_S, [_P, ctypes.c_int, ctypes.c_int, _P]),
     "nxc_dist_finalize": (_S, [_P]),
+    "nxc_dist_p2p_enabled": (ctypes.c_int, [_P]),
     "nxc_allreduce": (_S, [_P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "nxc_allreduce_async": (_S, [_P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "nxc_comm_wait": (_S, [_P]),

@@ -561,3 +561,56 @@ def matmul(x: Tensor, y: Tensor) -> Tensor:
     _call(x.context, "matmul", x.context._lib.nxc_matmul, ctypes.byref(do), ctypes.byref(dx),
           ctypes.byref(dy))
     return out
+
+
+# ---- fft family (backend_c/nx_backend.ml:502-549) -----------------------------------------
+# Unnormalised transforms; the binding owns the output shape and dtype, the engine reads only
+# the last entry of `s`.
+def _axes_arg(axes):
+    axes = [int(a) for a in axes]
+    return (ctypes.c_int * _b.max(len(axes), 1))(*axes), len(axes)
+
+
+def _fft(x: Tensor, axes, inverse: bool, opname: str) -> Tensor:
+    out = _create(x.context, x.dtype, x.shape)
+    ax, n = _axes_arg(axes)
+    if n == 0 and out.buffer.nbytes:
+        # nothing is transformed and nothing written: the reference's calloc'ed output stays zero
+        check(x.context.ptr, opname, x.context._lib.nxc_memset(x.context.ptr, out.buffer.ptr, 0, out.buffer.nbytes))
+    do, dx = out._desc(), x._desc()
+    _call(x.context, opname, x.context._lib.nxc_fft, ctypes.byref(do), ctypes.byref(dx), ax, n, 1 if inverse else 0)
+    return out
+
+
+def fft(x: Tensor, axes) -> Tensor:
+    return _fft(x, axes, False, "fft")
+
+
+def ifft(x: Tensor, axes) -> Tensor:
+    return _fft(x, axes, True, "ifft")
+
+
+def rfft(x: Tensor, dtype, axes) -> Tensor:
+    axes = [int(a) for a in axes]
+    last = axes[-1]
+    shape = list(x.shape)
+    shape[last] = x.shape[last] // 2 + 1
+    out = _create(x.context, _dt.of(dtype), shape)
+    ax, n = _axes_arg(axes)
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "rfft", x.context._lib.nxc_rfft, ctypes.byref(do), ctypes.byref(dx), ax, n)
+    return out
+
+
+def irfft(x: Tensor, dtype, axes, s=None) -> Tensor:
+    axes = [int(a) for a in axes]
+    last = axes[-1]
+    size = int(s[-1]) if s is not None else (x.shape[last] - 1) * 2
+    shape = list(x.shape)
+    shape[last] = size
+    out = _create(x.context, _dt.of(dtype), shape)
+    ax, n = _axes_arg(axes)
+    do, dx = out._desc(), x._desc()
+    _call(x.context, "irfft", x.context._lib.nxc_irfft, ctypes.byref(do), ctypes.byref(dx), ax, n,
+          int(s[-1]) if s is not None else 0)
+    return out

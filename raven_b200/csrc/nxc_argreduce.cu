@@ -4,6 +4,8 @@
 // strict comparison so ties keep the FIRST index; the first NaN wins. The
 // (value, index) pair makes the combine associative and order-free, so the
 // split-and-fold kernels of nxc_fold.cuh give the sequential answer exactly.
+#include <limits>
+
 #include "nxc_ops.cuh"
 #include "nxc_fold.cuh"
 
@@ -17,14 +19,30 @@ template <int IS_MAX, int DT> struct ArgP {
   typedef ArgAcc<C> A;
   static constexpr int cls = D::cls;
   static constexpr bool ok = (cls != NXC_CLS_COMPLEX);
-  __device__ __forceinline__ static A identity() { A a; a.v = C(); a.idx = -1; return a; }
+  // An accumulator that has taken nothing yet has idx < 0. Floats start from NaN so that the
+  // one-instruction "greater or unordered" test sends the first element (and any NaN) to the
+  // exact rule below; integers start from the weakest value, never take an equal element, and
+  // an output that ends with idx < 0 saw only that value: its answer is index 0 (finish).
+  __device__ __forceinline__ static A identity() {
+    A a;
+    a.idx = -1;
+    if constexpr (cls == NXC_CLS_FLOAT) a.v = (C)NAN;
+    else if constexpr (cls == NXC_CLS_BOOL) a.v = IS_MAX ? (C)0 : (C)1;
+    else a.v = IS_MAX ? std::numeric_limits<C>::lowest() : std::numeric_limits<C>::max();
+    return a;
+  }
   // one element, visited in increasing index order per accumulator: a strict
   // comparison keeps the first of equals, the NaN clause lets the first NaN win
   __device__ __forceinline__ static void step(A &acc, S s, int64_t r) {
     const C v = D::ld(s);
-    bool take = IS_MAX ? (v > acc.v) : (v < acc.v);
-    if constexpr (cls == NXC_CLS_FLOAT) take = take || ((v != v) && !(acc.v != acc.v));
-    if (take || acc.idx < 0) { acc.v = v; acc.idx = (int32_t)r; }
+    if constexpr (cls == NXC_CLS_FLOAT) {
+      if (!(IS_MAX ? (v <= acc.v) : (v >= acc.v))) {  // v better, or v / acc NaN (acc NaN: empty or stuck)
+        const bool take = acc.idx < 0 || (IS_MAX ? (v > acc.v) : (v < acc.v)) || ((v != v) && !(acc.v != acc.v));
+        if (take) { acc.v = v; acc.idx = (int32_t)r; }
+      }
+    } else {
+      if (IS_MAX ? (v > acc.v) : (v < acc.v)) { acc.v = v; acc.idx = (int32_t)r; }
+    }
   }
   __device__ __forceinline__ static A combine(A a, A b) {
     if (a.idx < 0) return b;
@@ -43,7 +61,7 @@ template <int IS_MAX, int DT> struct ArgP {
     if (b_better) return b;
     return a_first ? a : b;
   }
-  __device__ __forceinline__ static SO finish(A a) { return a.idx; }
+  __device__ __forceinline__ static SO finish(A a) { return a.idx < 0 ? 0 : a.idx; }
 };
 
 extern "C" nxc_status nxc_argreduce(nxc_ctx *ctx, int is_max, const nxc_tensor *out,

@@ -39,6 +39,7 @@
 #define NXC_ERR_NO_DEVICE "no CUDA device available (this backend has no CPU fallback)"
 #define NXC_ERR_NCCL "NCCL error"
 #define NXC_ERR_BAD_OP "unknown operation code"
+#define NXC_ERR_TOO_LARGE "iteration space exceeds the launch grid"
 #define NXC_ERR_INDEX_DTYPE "indices must be int32"
 
 struct nxc_ctx {
@@ -55,6 +56,8 @@ struct nxc_ctx {
   // NCCL (dlopen'ed), see nxc_dist.cu
   void *nccl_comm;
   int rank, world;
+  // peer-memory mailboxes for small exchanges (CUDA IPC over NVLink), see nxc_dist.cu
+  struct nxc_p2p *p2p;
   // TMA descriptor encoder (driver entry point fetched at runtime)
   void *encode_tiled;
   // Side streams (created on first use): pinned host->device and device->host copies run on

@@ -55,6 +55,9 @@ static nxc_status nccl_load(nxc_ctx *ctx) {
   return NXC_OK;
 }
 
+static void nxc_p2p_setup(nxc_ctx *ctx);
+static void nxc_p2p_teardown(nxc_ctx *ctx);
+
 static nxc_status nccl_fail(nxc_ctx *ctx, ncclResult_t r, const char *what) {
   if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s: %s (%s)", NXC_ERR_NCCL, g_nccl.GetErrorString(r), what);
   return NXC_ERR_NCCL;
@@ -82,6 +85,7 @@ extern "C" nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const voi
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->world = world;
+  nxc_p2p_setup(ctx);
   return NXC_OK;
 }
 
@@ -89,9 +93,202 @@ extern "C" nxc_status nxc_dist_finalize(nxc_ctx *ctx) {
   if (ctx->nccl_comm) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    nxc_p2p_teardown(ctx);
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = NULL;
   }
+  return NXC_OK;
+}
+
+// ---- small exchanges over peer memory ----------------------------------------------------
+// The exchange step of a sharded reduction moves a few bytes to a few KB per rank; through
+// NCCL that is one ~10-20 us kernel per call and the sharded step is made of five of them.
+// Here every rank owns a MAILBOX (plain cudaMalloc, exported with CUDA IPC and mapped by every
+// peer at nxc_dist_init), and one kernel does the whole all-gather: CTA (s, c) stores chunk c
+// of this rank's payload straight into peer s's mailbox over NVLink, releases a flag there,
+// then waits for chunk c from rank s in its OWN mailbox and copies it to the output. Slots and
+// flags are double-buffered on the parity of a per-context epoch: a slot is rewritten at epoch
+// e+2, which a sender can only reach after it saw this rank's epoch e+1 flags, i.e. after this
+// rank finished reading epoch e. allreduce = this all-gather + the backend's own reduce over
+// the rank axis, in rank order on every rank, so all ranks hold bit-identical results (NCCL
+// promises that only per algorithm choice). Payloads above the slot size, async (comm-stream)
+// collectives and NX_CUDA_P2P=0 use NCCL.
+#define NXC_P2P_MAX_WORLD 16
+#define NXC_P2P_SLOT_BYTES ((size_t)256 << 10)
+#define NXC_P2P_CHUNK_BYTES ((size_t)16 << 10)
+#define NXC_P2P_MAX_CHUNKS (NXC_P2P_SLOT_BYTES / NXC_P2P_CHUNK_BYTES)
+
+struct nxc_p2p {
+  int world, rank;
+  char *local;                      // this rank's mailbox
+  char *peer[NXC_P2P_MAX_WORLD];    // every rank's mailbox as mapped here (peer[rank] == local)
+  uint32_t epoch;
+  int *status;                      // device word: nonzero after a wait timed out
+};
+struct NxcP2PArgs {
+  char *peer[NXC_P2P_MAX_WORLD];
+  int world, rank;
+  uint32_t epoch;
+  int chunks;
+  int64_t bytes;                    // payload per rank
+  const char *send;
+  char *recv;                       // [world][bytes]
+  int *status;
+};
+static __host__ __device__ inline size_t nxc_p2p_data_bytes(int world) { return 2 * (size_t)world * NXC_P2P_SLOT_BYTES; }
+static inline size_t nxc_p2p_total_bytes(int world) {
+  return nxc_p2p_data_bytes(world) + 2 * (size_t)world * NXC_P2P_MAX_CHUNKS * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ void nxc_st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t nxc_ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t nxc_globaltimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(256) nxc_p2p_allgather_kernel(const NxcP2PArgs a) {
+  const int s = blockIdx.x / a.chunks, c = blockIdx.x - s * a.chunks;
+  const int par = a.epoch & 1;
+  const int64_t lo = (int64_t)c * (int64_t)NXC_P2P_CHUNK_BYTES;
+  int64_t len = a.bytes - lo;
+  if (len > (int64_t)NXC_P2P_CHUNK_BYTES) len = NXC_P2P_CHUNK_BYTES;
+  const size_t flags_off = nxc_p2p_data_bytes(a.world);
+  // push: my chunk c -> peer s, slot [par][my rank]
+  {
+    char *dst = a.peer[s] + ((size_t)(par * a.world + a.rank)) * NXC_P2P_SLOT_BYTES + lo;
+    const char *src = a.send + lo;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const int64_t nv = len >> 4;
+      for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
+      for (int64_t i = (nv << 4) + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+    } else {
+      for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t *flag = (uint32_t *)(a.peer[s] + flags_off) + ((size_t)(par * a.world + a.rank)) * NXC_P2P_MAX_CHUNKS + c;
+      nxc_st_release_sys(flag, a.epoch);
+    }
+  }
+  // pull: chunk c of rank s has to land in my mailbox
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const uint32_t *flag = (const uint32_t *)(a.peer[a.rank] + flags_off) + ((size_t)(par * a.world + s)) * NXC_P2P_MAX_CHUNKS + c;
+    const uint64_t t0 = nxc_globaltimer();
+    int good = 1;
+    while (nxc_ld_acquire_sys(flag) != a.epoch) {
+      __nanosleep(64);
+      if (nxc_globaltimer() - t0 > 20000000000ull) { good = 0; atomicExch(a.status, 1); break; }  // 20 s: a peer died
+    }
+    ok = good;
+  }
+  __syncthreads();
+  if (!ok) return;
+  {
+    const char *src = a.peer[a.rank] + ((size_t)(par * a.world + s)) * NXC_P2P_SLOT_BYTES + lo;
+    char *dst = a.recv + (int64_t)s * a.bytes + lo;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const int64_t nv = len >> 4;
+      for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4 *)dst)[i] = __ldcv((const uint4 *)src + i);
+      for (int64_t i = (nv << 4) + threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcv(src + i);
+    } else {
+      for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcv(src + i);
+    }
+  }
+}
+
+static void nxc_p2p_teardown(nxc_ctx *ctx) {
+  nxc_p2p *q = ctx->p2p;
+  if (!q) return;
+  for (int r = 0; r < q->world; r++)
+    if (r != q->rank && q->peer[r]) cudaIpcCloseMemHandle(q->peer[r]);
+  if (q->local) cudaFree(q->local);
+  if (q->status) cudaFree(q->status);
+  free(q);
+  ctx->p2p = NULL;
+  cudaGetLastError();
+}
+
+// Collective: every rank calls it right after ncclCommInitRank. Failure at any step (no peer
+// access, IPC refused by the container) is not an error: ALL ranks then stay on NCCL -- the
+// decision is taken jointly through an allreduce(min) of the local outcome.
+static void nxc_p2p_setup(nxc_ctx *ctx) {
+  const char *env = getenv("NX_CUDA_P2P");
+  int want = !(env && env[0] == '0') && ctx->world > 1 && ctx->world <= NXC_P2P_MAX_WORLD;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  nxc_p2p *q = (nxc_p2p *)calloc(1, sizeof *q);
+  int good = want && q != NULL;
+  struct Xch { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  Xch *dev = NULL, *host = (Xch *)calloc(ctx->world, sizeof(Xch));
+  Xch mine;
+  memset(&mine, 0, sizeof mine);
+  if (good) {
+    q->world = ctx->world; q->rank = ctx->rank;
+    good = cudaMalloc(&q->local, nxc_p2p_total_bytes(ctx->world)) == cudaSuccess &&
+           cudaMemset(q->local, 0, nxc_p2p_total_bytes(ctx->world)) == cudaSuccess &&
+           cudaMalloc(&q->status, sizeof(int)) == cudaSuccess && cudaMemset(q->status, 0, sizeof(int)) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine.h, q->local) == cudaSuccess;
+  }
+  mine.ok = good;
+  // the handles travel through NCCL (every rank takes part, whatever its local outcome)
+  bool xch = host && cudaMalloc(&dev, sizeof(Xch) * ctx->world) == cudaSuccess &&
+             cudaMemcpy(dev + ctx->rank, &mine, sizeof mine, cudaMemcpyHostToDevice) == cudaSuccess &&
+             g_nccl.AllGather(dev + ctx->rank, dev, sizeof(Xch), ncclUint8, comm, ctx->stream) == 0 &&
+             cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+             cudaMemcpy(host, dev, sizeof(Xch) * ctx->world, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!xch) good = 0;
+  for (int r = 0; good && r < ctx->world; r++)
+    if (!host[r].ok) good = 0;
+  for (int r = 0; good && r < ctx->world; r++) {
+    if (r == ctx->rank) { q->peer[r] = q->local; continue; }
+    void *m = NULL;
+    if (cudaIpcOpenMemHandle(&m, host[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) good = 0;
+    q->peer[r] = (char *)m;
+  }
+  // joint verdict: min over ranks of `good` (mapping can fail on one rank only)
+  int *vd = (int *)dev;
+  if (xch && cudaMemcpy(vd, &good, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+      g_nccl.AllReduce(vd, vd, 1, ncclInt32, ncclMin, comm, ctx->stream) == 0 &&
+      cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+    int all = 0;
+    if (cudaMemcpy(&all, vd, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) all = 0;
+    good = good && all;
+  } else {
+    good = 0;
+  }
+  cudaGetLastError();
+  if (dev) cudaFree(dev);
+  free(host);
+  ctx->p2p = q;
+  if (!good) nxc_p2p_teardown(ctx);
+}
+
+extern "C" int nxc_dist_p2p_enabled(nxc_ctx *ctx) { return ctx->p2p != NULL; }
+
+static nxc_status nxc_p2p_allgather(nxc_ctx *ctx, const void *send, void *recv, int64_t bytes) {
+  nxc_p2p *q = ctx->p2p;
+  NxcP2PArgs a;
+  for (int r = 0; r < q->world; r++) a.peer[r] = q->peer[r];
+  a.world = q->world; a.rank = q->rank;
+  a.epoch = ++q->epoch;
+  if (a.epoch == 0) a.epoch = ++q->epoch;  // 0 is the cleared-flag value
+  a.chunks = (int)((bytes + (int64_t)NXC_P2P_CHUNK_BYTES - 1) / (int64_t)NXC_P2P_CHUNK_BYTES);
+  if (a.chunks < 1) a.chunks = 1;
+  a.bytes = bytes;
+  a.send = (const char *)send;
+  a.recv = (char *)recv;
+  a.status = q->status;
+  nxc_p2p_allgather_kernel<<<q->world * a.chunks, 256, 0, ctx->stream>>>(a);
+  NXC_LAUNCH_CHECK(ctx);
   return NXC_OK;
 }
 
@@ -114,6 +311,27 @@ static int nccl_dtype(int dt) {
 static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op, cudaStream_t stream);
 
 extern "C" nxc_status nxc_allreduce(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+  const int64_t bytes = count * nxc_elem_size(dtype);
+  if (ctx->p2p && count > 0 && bytes > 0 && (size_t)bytes <= NXC_P2P_SLOT_BYTES && op >= 0 && op <= NXC_RMIN &&
+      nccl_dtype(dtype) >= 0 && dtype != NXC_BOOL) {
+    // gather the partials over peer memory, fold them in rank order with the backend's reduce
+    void *g = NULL;
+    nxc_status s = nxc_alloc(ctx, (size_t)bytes * ctx->world, &g);
+    if (s) return s;
+    s = nxc_p2p_allgather(ctx, buf, g, bytes);
+    if (!s) {
+      nxc_tensor in, out;
+      memset(&in, 0, sizeof in);
+      memset(&out, 0, sizeof out);
+      in.data = g; in.dtype = dtype; in.ndim = 2;
+      in.shape[0] = ctx->world; in.shape[1] = count; in.strides[0] = count; in.strides[1] = 1;
+      out.data = buf; out.dtype = dtype; out.ndim = 1; out.shape[0] = count; out.strides[0] = 1;
+      const int axis = 0;
+      s = nxc_reduce(ctx, op, &out, &in, &axis, 1);
+    }
+    nxc_status f = nxc_free(ctx, g);
+    return s ? s : f;
+  }
   return allreduce_on(ctx, buf, count, dtype, op, ctx->stream);
 }
 extern "C" nxc_status nxc_allreduce_async(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
@@ -145,6 +363,8 @@ static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype
 
 extern "C" nxc_status nxc_allgather(nxc_ctx *ctx, const void *send, void *recv, int64_t bytes_per_rank) {
   if (!ctx->nccl_comm) { snprintf(ctx->err, sizeof ctx->err, "%s: nxc_dist_init not called", NXC_ERR_NCCL); return NXC_ERR_NCCL; }
+  if (ctx->p2p && bytes_per_rank > 0 && (size_t)bytes_per_rank <= NXC_P2P_SLOT_BYTES)
+    return nxc_p2p_allgather(ctx, send, recv, bytes_per_rank);
   ncclResult_t r = g_nccl.AllGather(send, recv, (size_t)bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
   if (r) return nccl_fail(ctx, r, "ncclAllGather");
   ctx->launches++;

@@ -1,0 +1,480 @@
+// nxc_fft.cu -- fft / ifft / rfft / irfft.
+// Replaces caml_nx_c_fft / caml_nx_c_ifft / caml_nx_c_rfft / caml_nx_c_irfft (reference:
+// nx_c_fft.c:1173-1223; drivers nx_c_fft.c:940-1143; per-axis pass nx_c_fft.c:869-936).
+//
+// What is kept from the reference is the CONTRACT: transforms are unnormalised (fft is the
+// -sign DFT, ifft the +sign DFT without 1/n; nx_c_fft.c:38-41), everything computes in double
+// (c32 / f32 upcast on gather and round once on store), multi-axis = one 1-D pass per axis in
+// the reference's order (fft: axes order, first pass reads `in`, later ones `out` in place;
+// rfft: the last axis first, real -> half spectrum, then the others; irfft: the other axes in
+// a c64 temporary, then half spectrum -> real with Hermitian reconstruction and zero-padding /
+// truncation to `s`), any length n is accepted.
+//
+// How it is computed is not the reference's (a CPU mixed-radix Cooley-Tukey with per-thread
+// line scratch): each axis pass is gather -> transform -> scatter over ALL lines at once.
+//   gather   one thread per (line, k): strided read, convert to double complex, into a
+//            contiguous [lines][m] work buffer
+//   core     power-of-two self-sorting (Stockham) radix-2 transform of every line: one CTA
+//            per line with both ping-pong buffers in shared memory when m <= 4096, else
+//            log2(m) global passes over the whole buffer
+//   other n  Bluestein's chirp-z on top of the same core (m = next power of two >= 2n-1):
+//            chirp multiply in the gather, pointwise product with the transformed filter,
+//            inverse core transform, chirp multiply and 1/m in the scatter
+//   scatter  one thread per (line, k < n_out): convert to the output type, strided write
+// Twiddles are sincospi() of an exactly reduced rational angle in double precision.
+#include "nxc_common.cuh"
+#include "nxc_map.cuh"
+
+#define NXC_FFT_SMEM_MAX 4096
+
+struct NxcFftLines {
+  int n;  // dims other than the transform axis
+  NxcFastDiv div[NXC_MAX_NDIM];
+  int64_t shape[NXC_MAX_NDIM];
+  int64_t src_stride[NXC_MAX_NDIM];
+  int64_t dst_stride[NXC_MAX_NDIM];
+  int small;
+};
+
+__device__ __forceinline__ void nxc_fft_line_base(const NxcFftLines &d, int64_t L, int64_t &so, int64_t &dof) {
+  so = 0;
+  dof = 0;
+  if (d.small) {
+    uint32_t r = (uint32_t)L;
+    for (int i = d.n - 1; i >= 0; i--) {
+      const uint32_t q = nxc_fastdiv(r, d.div[i]);
+      const uint32_t c = r - q * d.div[i].d;
+      so += (int64_t)c * d.src_stride[i];
+      dof += (int64_t)c * d.dst_stride[i];
+      r = q;
+    }
+  } else {
+    int64_t r = L;
+    for (int i = d.n - 1; i >= 0; i--) {
+      const int64_t q = r / d.shape[i];
+      const int64_t c = r - q * d.shape[i];
+      so += c * d.src_stride[i];
+      dof += c * d.dst_stride[i];
+      r = q;
+    }
+  }
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// exp(sign * i * pi * num / den), 0 <= num < 2*den
+__device__ __forceinline__ double2 cispi(int sign, int64_t num, int64_t den) {
+  double s, c;
+  sincospi((double)num / (double)den, &s, &c);
+  return make_double2(c, sign < 0 ? -s : s);
+}
+// Bluestein chirp w[k] = exp(sign * i * pi * k^2 / n), k^2 reduced mod 2n (reference:
+// nx_c_fft.c:656-663)
+__device__ __forceinline__ double2 chirp_at(int sign, int64_t k, int64_t n) {
+  const unsigned long long kk = ((unsigned long long)k * (unsigned long long)k) % (unsigned long long)(2 * n);
+  return cispi(sign, (int64_t)kk, n);
+}
+
+enum { NXC_FFT_SRC_C32 = 0, NXC_FFT_SRC_C64 = 1, NXC_FFT_SRC_F32 = 2, NXC_FFT_SRC_F64 = 3 };
+
+struct NxcFftGather {
+  NxcFftLines lines;
+  const void *src;
+  double2 *work;
+  int64_t n_lines;
+  int64_t n;        // logical line length fed to the transform
+  int64_t n_src;    // elements present in the source line (irfft: usable half-spectrum bins)
+  int64_t m;        // work line length (n, or Bluestein's power of two)
+  int64_t stride;   // source stride along the axis (elements)
+  int src_kind;
+  int sign;
+  int bluestein;
+  int hermitian;    // irfft last axis: rebuild the length-n spectrum from n_src bins
+};
+
+__device__ __forceinline__ double2 nxc_fft_read(const void *src, int kind, int64_t off) {
+  switch (kind) {
+    case NXC_FFT_SRC_C32: { const float2 z = ((const float2 *)src)[off]; return make_double2((double)z.x, (double)z.y); }
+    case NXC_FFT_SRC_C64: return ((const double2 *)src)[off];
+    case NXC_FFT_SRC_F32: return make_double2((double)((const float *)src)[off], 0.0);
+    default: return make_double2(((const double *)src)[off], 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(256) nxc_fft_gather_kernel(const __grid_constant__ NxcFftGather g) {
+  const int64_t total = g.n_lines * g.m;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t L = i / g.m, k = i - L * g.m;
+    double2 v = make_double2(0.0, 0.0);
+    if (k < g.n) {
+      int64_t so, dof;
+      nxc_fft_line_base(g.lines, L, so, dof);
+      if (!g.hermitian) {
+        if (k < g.n_src) v = nxc_fft_read(g.src, g.src_kind, so + k * g.stride);
+      } else if (k < g.n_src) {
+        v = nxc_fft_read(g.src, g.src_kind, so + k * g.stride);
+      } else {
+        // conjugate mirror of bin n-k when that bin was supplied (reference: nx_c_fft.c:1014-1021)
+        const int64_t q = g.n - k;
+        if (q >= 1 && q < g.n_src && q != k) {
+          v = nxc_fft_read(g.src, g.src_kind, so + q * g.stride);
+          v.y = -v.y;
+        }
+      }
+      if (g.bluestein) v = cmul(v, chirp_at(g.sign, k, g.n));
+    }
+    g.work[i] = v;
+  }
+}
+
+struct NxcFftScatter {
+  NxcFftLines lines;
+  void *dst;
+  const double2 *work;
+  int64_t n_lines;
+  int64_t n, n_out, m;
+  int64_t stride;  // destination stride along the axis
+  int dst_kind;
+  int sign;
+  int bluestein;
+};
+
+__global__ void __launch_bounds__(256) nxc_fft_scatter_kernel(const __grid_constant__ NxcFftScatter g) {
+  const int64_t total = g.n_lines * g.n_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t L = i / g.n_out, k = i - L * g.n_out;
+    double2 v = g.work[L * g.m + k];
+    if (g.bluestein) {
+      v = cmul(v, chirp_at(g.sign, k, g.n));
+      const double inv = 1.0 / (double)g.m;
+      v.x *= inv;
+      v.y *= inv;
+    }
+    int64_t so, dof;
+    nxc_fft_line_base(g.lines, L, so, dof);
+    const int64_t off = dof + k * g.stride;
+    switch (g.dst_kind) {
+      case NXC_FFT_SRC_C32: ((float2 *)g.dst)[off] = make_float2((float)v.x, (float)v.y); break;
+      case NXC_FFT_SRC_C64: ((double2 *)g.dst)[off] = v; break;
+      case NXC_FFT_SRC_F32: ((float *)g.dst)[off] = (float)v.x; break;
+      default: ((double *)g.dst)[off] = v.x; break;
+    }
+  }
+}
+
+// ---- the power-of-two core -------------------------------------------------------------------
+// Stockham radix-2, stage Ns = 1, 2, 4, ...: butterfly j (0 <= j < m/2) reads in[j], in[j + m/2],
+// twiddles the second by exp(sign*i*pi*(j mod Ns)/Ns), and writes a+b, a-b to
+// out[(j div Ns)*2Ns + j mod Ns] and Ns further: the output of the last stage is in natural order.
+__global__ void nxc_fft_smem_kernel(double2 *__restrict__ work, int64_t m, int log2m, int sign) {
+  extern __shared__ double2 fsm[];
+  double2 *a = fsm, *b = fsm + m;
+  double2 *line = work + (int64_t)blockIdx.x * m;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) a[i] = line[i];
+  __syncthreads();
+  const int64_t half = m >> 1;
+  for (int st = 0; st < log2m; st++) {
+    const int64_t Ns = (int64_t)1 << st;
+    for (int64_t j = threadIdx.x; j < half; j += blockDim.x) {
+      const int64_t k = j & (Ns - 1);
+      const double2 u0 = a[j];
+      const double2 u1 = cmul(a[j + half], cispi(sign, k, Ns));
+      const int64_t j0 = ((j - k) << 1) + k;
+      b[j0] = make_double2(u0.x + u1.x, u0.y + u1.y);
+      b[j0 + Ns] = make_double2(u0.x - u1.x, u0.y - u1.y);
+    }
+    __syncthreads();
+    double2 *t = a; a = b; b = t;
+  }
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) line[i] = a[i];
+}
+
+__global__ void __launch_bounds__(256)
+nxc_fft_global_pass_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, int64_t n_lines, int64_t m,
+                           int st, int sign) {
+  const int64_t half = m >> 1, total = n_lines * half;
+  const int64_t Ns = (int64_t)1 << st;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t L = i / half, j = i - L * half;
+    const double2 *a = in + L * m;
+    double2 *b = out + L * m;
+    const int64_t k = j & (Ns - 1);
+    const double2 u0 = a[j];
+    const double2 u1 = cmul(a[j + half], cispi(sign, k, Ns));
+    const int64_t j0 = ((j - k) << 1) + k;
+    b[j0] = make_double2(u0.x + u1.x, u0.y + u1.y);
+    b[j0 + Ns] = make_double2(u0.x - u1.x, u0.y - u1.y);
+  }
+}
+
+// Bluestein filter b[k] = conj(w[k]) for |k| < n, circular over m, zero elsewhere
+__global__ void __launch_bounds__(256) nxc_fft_filter_kernel(double2 *bf, int64_t n, int64_t m, int sign) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x) {
+    double2 v = make_double2(0.0, 0.0);
+    int64_t q = -1;
+    if (k < n) q = k;
+    else if (m - k < n) q = m - k;
+    if (q >= 0) { v = chirp_at(sign, q, n); v.y = -v.y; }
+    bf[k] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+nxc_fft_pointwise_kernel(double2 *work, const double2 *__restrict__ bf, int64_t n_lines, int64_t m) {
+  const int64_t total = n_lines * m;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    work[i] = cmul(work[i], bf[i % m]);
+}
+
+static unsigned nxc_fft_grid(nxc_ctx *ctx, int64_t items) {
+  int64_t b = (items + 255) / 256;
+  const int64_t cap = (int64_t)ctx->sm_count * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// In-place transform of n_lines contiguous lines of power-of-two length m. `tmp` is a second
+// buffer of the same size (only used when m > NXC_FFT_SMEM_MAX).
+static nxc_status nxc_fft_core(nxc_ctx *ctx, double2 *work, double2 *tmp, int64_t n_lines, int64_t m, int sign) {
+  int log2m = 0;
+  while (((int64_t)1 << log2m) < m) log2m++;
+  if (log2m == 0) return NXC_OK;
+  if (m <= NXC_FFT_SMEM_MAX) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_fft_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             2 * NXC_FFT_SMEM_MAX * (int)sizeof(double2)));
+      attr_set = true;
+    }
+    int threads = (int)(m / 2);
+    if (threads < 32) threads = 32;
+    if (threads > 512) threads = 512;
+    for (int64_t l0 = 0; l0 < n_lines; l0 += 0x40000000) {  // grid.x limit
+      const int64_t nl = n_lines - l0 < 0x40000000 ? n_lines - l0 : 0x40000000;
+      nxc_fft_smem_kernel<<<(unsigned)nl, threads, 2 * m * sizeof(double2), ctx->stream>>>(work + l0 * m, m, log2m, sign);
+      NXC_LAUNCH_CHECK(ctx);
+    }
+    return NXC_OK;
+  }
+  double2 *a = work, *b = tmp;
+  for (int st = 0; st < log2m; st++) {
+    nxc_fft_global_pass_kernel<<<nxc_fft_grid(ctx, n_lines * (m / 2)), 256, 0, ctx->stream>>>(a, b, n_lines, m, st, sign);
+    NXC_LAUNCH_CHECK(ctx);
+    double2 *t = a; a = b; b = t;
+  }
+  if (a != work) NXC_CUDA_TRY(ctx, cudaMemcpyAsync(work, a, sizeof(double2) * (size_t)(n_lines * m), cudaMemcpyDeviceToDevice, ctx->stream));
+  return NXC_OK;
+}
+
+struct NxcFftPass {
+  const nxc_tensor *src, *dst;
+  int src_kind, dst_kind;
+  int axis;
+  int64_t n;       // transform length
+  int64_t n_src;   // source bins read per line
+  int64_t n_out;   // elements written per line
+  int sign;
+  int hermitian;
+};
+
+static int64_t nxc_fft_esize(int kind) { return kind == NXC_FFT_SRC_C64 ? 16 : (kind == NXC_FFT_SRC_F32 ? 4 : 8); }
+
+// One axis pass over all lines (reference: run_axis, nx_c_fft.c:896-936).
+static nxc_status nxc_fft_pass(nxc_ctx *ctx, const NxcFftPass &p) {
+  const nxc_tensor *src = p.src, *dst = p.dst;
+  int64_t n_lines = 1;
+  NxcFftLines ln;
+  ln.n = 0;
+  for (int d = 0; d < dst->ndim; d++) {
+    if (d == p.axis) continue;
+    n_lines *= dst->shape[d];
+    ln.shape[ln.n] = dst->shape[d];
+    ln.src_stride[ln.n] = src->strides[d];
+    ln.dst_stride[ln.n] = dst->strides[d];
+    ln.n++;
+  }
+  if (n_lines == 0 || p.n == 0 || p.n_out == 0) return NXC_OK;
+  ln.small = n_lines < 0x7FFFFFFFLL;
+  for (int i = 0; i < ln.n; i++) ln.div[i] = nxc_fastdiv_make(ln.small ? (uint32_t)ln.shape[i] : 1u);
+  const bool pow2 = (p.n & (p.n - 1)) == 0;
+  int64_t m = p.n;
+  if (!pow2) {
+    m = 1;
+    while (m < 2 * p.n - 1) m <<= 1;
+  }
+  const size_t wbytes = sizeof(double2) * (size_t)n_lines * (size_t)m;
+  double2 *work = NULL, *tmp = NULL, *bf = NULL;
+  nxc_status s = nxc_alloc(ctx, wbytes, (void **)&work);
+  if (s) return s;
+  if (m > NXC_FFT_SMEM_MAX) s = nxc_alloc(ctx, wbytes, (void **)&tmp);
+  if (!s && !pow2) s = nxc_alloc(ctx, sizeof(double2) * (size_t)m * 2, (void **)&bf);
+  if (!s) {
+    NxcFftGather g;
+    g.lines = ln;
+    g.src = (const char *)src->data + src->offset * nxc_fft_esize(p.src_kind);
+    g.work = work;
+    g.n_lines = n_lines; g.n = p.n; g.n_src = p.n_src; g.m = m;
+    g.stride = src->strides[p.axis];
+    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = !pow2; g.hermitian = p.hermitian;
+    nxc_fft_gather_kernel<<<nxc_fft_grid(ctx, n_lines * m), 256, 0, ctx->stream>>>(g);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft gather");
+  }
+  if (!s) {
+    if (pow2) {
+      s = nxc_fft_core(ctx, work, tmp, n_lines, m, p.sign);
+    } else {
+      nxc_fft_filter_kernel<<<nxc_fft_grid(ctx, m), 256, 0, ctx->stream>>>(bf, p.n, m, p.sign);
+      ctx->launches++;
+      s = nxc_fft_core(ctx, bf, bf + m, 1, m, -1);
+      if (!s) s = nxc_fft_core(ctx, work, tmp, n_lines, m, -1);
+      if (!s) {
+        nxc_fft_pointwise_kernel<<<nxc_fft_grid(ctx, n_lines * m), 256, 0, ctx->stream>>>(work, bf, n_lines, m);
+        ctx->launches++;
+        s = nxc_fft_core(ctx, work, tmp, n_lines, m, +1);
+      }
+    }
+  }
+  if (!s) {
+    NxcFftScatter g;
+    g.lines = ln;
+    g.dst = (char *)dst->data + dst->offset * nxc_fft_esize(p.dst_kind);
+    g.work = work;
+    g.n_lines = n_lines; g.n = p.n; g.n_out = p.n_out; g.m = m;
+    g.stride = dst->strides[p.axis];
+    g.dst_kind = p.dst_kind; g.sign = p.sign; g.bluestein = !pow2;
+    nxc_fft_scatter_kernel<<<nxc_fft_grid(ctx, n_lines * p.n_out), 256, 0, ctx->stream>>>(g);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft scatter");
+  }
+  nxc_free(ctx, work);
+  if (tmp) nxc_free(ctx, tmp);
+  if (bf) nxc_free(ctx, bf);
+  return s;
+}
+
+static int nxc_fft_kind(int dt) {
+  switch (dt) {
+    case NXC_C32: return NXC_FFT_SRC_C32;
+    case NXC_C64: return NXC_FFT_SRC_C64;
+    case NXC_F32: return NXC_FFT_SRC_F32;
+    case NXC_F64: return NXC_FFT_SRC_F64;
+    default: return -1;
+  }
+}
+
+static nxc_status nxc_fft_fail(nxc_ctx *ctx, nxc_status s) {
+  if (s && strcmp(s, NXC_ERR_CUDA) != 0) snprintf(ctx->err, sizeof ctx->err, "%s", s);
+  return s;
+}
+
+// fft / ifft (reference: nx_c_fft_run, nx_c_fft.c:940-955; dtype gate nx_c_fft.c:1166)
+extern "C" nxc_status nxc_fft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes,
+                              int inverse) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_fft_fail(ctx, s);
+  if (in->dtype != NXC_C32 && in->dtype != NXC_C64) return nxc_fft_fail(ctx, NXC_ERR_BAD_KIND);
+  if (out->dtype != in->dtype || out->ndim != in->ndim) return nxc_fft_fail(ctx, NXC_ERR_SHAPE);
+  const int kind = nxc_fft_kind(in->dtype);
+  for (int ai = 0; ai < n_axes; ai++) {
+    const int axis = axes[ai];
+    if (axis < 0 || axis >= in->ndim) return nxc_fft_fail(ctx, NXC_ERR_AXIS);
+    NxcFftPass p;
+    p.src = ai == 0 ? in : out;
+    p.dst = out;
+    p.src_kind = p.dst_kind = kind;
+    p.axis = axis;
+    p.n = p.n_src = p.n_out = out->shape[axis];
+    p.sign = inverse ? 1 : -1;
+    p.hermitian = 0;
+    if ((s = nxc_fft_pass(ctx, p))) return nxc_fft_fail(ctx, s);
+  }
+  return NXC_OK;
+}
+
+// rfft (reference: nx_c_rfft_run, nx_c_fft.c:958-983)
+extern "C" nxc_status nxc_rfft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_fft_fail(ctx, s);
+  if ((in->dtype != NXC_F32 && in->dtype != NXC_F64) || (out->dtype != NXC_C32 && out->dtype != NXC_C64))
+    return nxc_fft_fail(ctx, NXC_ERR_BAD_KIND);
+  if (n_axes == 0) return NXC_OK;
+  if (out->ndim != in->ndim) return nxc_fft_fail(ctx, NXC_ERR_SHAPE);
+  const int last = axes[n_axes - 1];
+  if (last < 0 || last >= in->ndim) return nxc_fft_fail(ctx, NXC_ERR_AXIS);
+  const int64_t n = in->shape[last], half = n / 2 + 1;
+  if (out->shape[last] != half) return nxc_fft_fail(ctx, NXC_ERR_SHAPE);
+  NxcFftPass p;
+  p.src = in; p.dst = out;
+  p.src_kind = nxc_fft_kind(in->dtype); p.dst_kind = nxc_fft_kind(out->dtype);
+  p.axis = last; p.n = p.n_src = n; p.n_out = half; p.sign = -1; p.hermitian = 0;
+  if ((s = nxc_fft_pass(ctx, p))) return nxc_fft_fail(ctx, s);
+  for (int ai = 0; ai < n_axes - 1; ai++) {
+    const int axis = axes[ai];
+    if (axis < 0 || axis >= out->ndim) return nxc_fft_fail(ctx, NXC_ERR_AXIS);
+    p.src = out; p.dst = out;
+    p.src_kind = p.dst_kind = nxc_fft_kind(out->dtype);
+    p.axis = axis; p.n = p.n_src = p.n_out = out->shape[axis];
+    if ((s = nxc_fft_pass(ctx, p))) return nxc_fft_fail(ctx, s);
+  }
+  return NXC_OK;
+}
+
+// irfft (reference: nx_c_irfft_run, nx_c_fft.c:1029-1143). s_last <= 0 infers 2*(half-1).
+extern "C" nxc_status nxc_irfft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes,
+                                int64_t s_last) {
+  nxc_status st;
+  if ((st = nxc_check_tensor(in)) || (st = nxc_check_tensor(out))) return nxc_fft_fail(ctx, st);
+  if ((in->dtype != NXC_C32 && in->dtype != NXC_C64) || (out->dtype != NXC_F32 && out->dtype != NXC_F64))
+    return nxc_fft_fail(ctx, NXC_ERR_BAD_KIND);
+  if (n_axes == 0) return NXC_OK;
+  if (out->ndim != in->ndim) return nxc_fft_fail(ctx, NXC_ERR_SHAPE);
+  const int last = axes[n_axes - 1];
+  if (last < 0 || last >= in->ndim) return nxc_fft_fail(ctx, NXC_ERR_AXIS);
+  const int64_t in_half = in->shape[last];
+  const int64_t s = s_last > 0 ? s_last : 2 * (in_half - 1);
+  if (out->shape[last] != s) return nxc_fft_fail(ctx, NXC_ERR_SHAPE);
+  const int64_t needed_half = s / 2 + 1;
+  const int64_t half = in_half < needed_half ? in_half : needed_half;
+  for (int ai = 0; ai < n_axes - 1; ai++)
+    if (axes[ai] < 0 || axes[ai] >= in->ndim) return nxc_fft_fail(ctx, NXC_ERR_AXIS);
+
+  // the other transformed axes run in a contiguous c64 temporary of in's shape
+  const nxc_tensor *spec = in;
+  nxc_tensor tmp;
+  void *tdata = NULL;
+  int spec_kind = nxc_fft_kind(in->dtype);
+  if (n_axes > 1) {
+    tmp = *in;
+    int64_t nelem = 1;
+    for (int d = in->ndim - 1; d >= 0; d--) { tmp.strides[d] = nelem; nelem *= in->shape[d]; }
+    tmp.offset = 0;
+    tmp.dtype = NXC_C64;
+    if ((st = nxc_alloc(ctx, sizeof(double2) * (size_t)(nelem ? nelem : 1), &tdata))) return nxc_fft_fail(ctx, st);
+    tmp.data = tdata;
+    for (int ai = 0; ai < n_axes - 1 && !st; ai++) {
+      NxcFftPass p;
+      p.src = ai == 0 ? in : &tmp;
+      p.dst = &tmp;
+      p.src_kind = ai == 0 ? nxc_fft_kind(in->dtype) : NXC_FFT_SRC_C64;
+      p.dst_kind = NXC_FFT_SRC_C64;
+      p.axis = axes[ai];
+      p.n = p.n_src = p.n_out = in->shape[axes[ai]];
+      p.sign = 1;
+      p.hermitian = 0;
+      st = nxc_fft_pass(ctx, p);
+    }
+    spec = &tmp;
+    spec_kind = NXC_FFT_SRC_C64;
+  }
+  if (!st && s > 0) {
+    NxcFftPass p;
+    p.src = spec; p.dst = out;
+    p.src_kind = spec_kind; p.dst_kind = nxc_fft_kind(out->dtype);
+    p.axis = last; p.n = s; p.n_src = half; p.n_out = s; p.sign = 1; p.hermitian = 1;
+    st = nxc_fft_pass(ctx, p);
+  }
+  if (tdata) nxc_free(ctx, tdata);
+  return nxc_fft_fail(ctx, st);
+}

@@ -100,6 +100,18 @@ __device__ __forceinline__ A nxc_shfl_xor(const A &v, int mask) {
   return r.a;
 }
 
+// rows in flight per thread group on the short-row path: small accumulators afford 8
+template <class P> struct NxcFoldG { static constexpr int v = sizeof(typename P::A) <= 8 ? 8 : 4; };
+
+// offsets of output `o`: one kept dim (the usual [rows, R] case) is a multiplication, not a
+// decode -- cheap enough to redo at the store instead of keeping per-row offsets in registers
+__device__ __forceinline__ void nxc_kept_offset(const NxcDimList &d, int64_t o, bool small, int64_t &in_off,
+                                                int64_t &out_off) {
+  if (d.n == 0) { in_off = 0; out_off = 0; }
+  else if (d.n == 1) { in_off = o * d.in_stride[0]; out_off = o * d.out_stride[0]; }
+  else nxc_dims_offset(d, o, small, in_off, out_off);
+}
+
 // ---- row kernel ------------------------------------------------------------------
 // P: reduction policy with
 //   typedef S (input storage), A (accumulator), SO (output storage)
@@ -121,55 +133,6 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
   const int split = (int)((int64_t)blockIdx.x - rowblock * a.S);
   const int64_t o = rowblock * RPB + row_in_block;
   const bool live = o < a.O;
-  // Short rows (fewer than 256 work items per output, no split): one thread group folds G
-  // adjacent-by-group rows at once so G independent vector loads are in flight per thread.
-  if (a.G > 1) {
-    constexpr int G = 4;
-    A accg[G];
-    int64_t ib[G], ob[G];
-    bool lv[G];
-    const int64_t o_base = rowblock * ((int64_t)RPB * G) + row_in_block;
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      accg[g] = P::identity();
-      const int64_t og = o_base + (int64_t)g * RPB;
-      lv[g] = og < a.O;
-      ib[g] = 0; ob[g] = 0;
-      if (lv[g]) nxc_dims_offset(a.kept, og, a.small, ib[g], ob[g]);
-    }
-    const int64_t stepg = (int64_t)TPR * VEC;
-    for (int64_t r = (int64_t)tr * VEC; r < a.R; r += stepg) {
-      S v[G][VEC];
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        if (lv[g]) {
-          if (VEC > 1) nxc_load_vec<S, VEC>(in + ib[g] + r, v[g]);
-          else v[g][0] = in[ib[g] + r * a.s_inner];
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < G; g++)
-        if (lv[g]) {
-#pragma unroll
-          for (int j = 0; j < VEC; j++) P::step(accg[g], v[g][j], r + j);
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      A t = accg[g];
-      if (TPR <= 32) {
-        for (int m = TPR >> 1; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
-      } else {
-        for (int m = 16; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
-        __syncthreads();
-        sm[threadIdx.x] = t;
-        __syncthreads();
-        if (tr == 0) for (int w = 32; w < TPR; w += 32) t = P::combine(t, sm[threadIdx.x + w]);
-      }
-      if (lv[g] && tr == 0) out[ob[g]] = P::finish(t);
-    }
-    return;
-  }
   A acc[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) acc[i] = P::identity();
@@ -237,6 +200,68 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
   }
 }
 
+// ---- short-row kernel ---------------------------------------------------------------
+template <class P, int VEC>
+__global__ void __launch_bounds__(NXC_FOLD_THREADS)
+nxc_fold_short_kernel(const typename P::S *__restrict__ in, typename P::SO *__restrict__ out,
+                      const __grid_constant__ NxcRowArgs a) {
+  typedef typename P::S S;
+  typedef typename P::A A;
+  __shared__ A sm[NXC_FOLD_THREADS];
+  const int TPR = 1 << a.tpr_log2;
+  const int RPB = NXC_FOLD_THREADS >> a.tpr_log2;
+  const int tr = threadIdx.x & (TPR - 1);
+  const int row_in_block = threadIdx.x >> a.tpr_log2;
+  const int64_t rowblock = (int64_t)blockIdx.x;
+// Short rows (fewer than 256 work items per output, no split): one thread group folds G rows
+// at once (rows RPB apart), so G independent vector loads are in flight per thread and
+// iteration -- 128 bytes for the 4-byte types, what the flat map kernel keeps in flight.
+  constexpr int G = NxcFoldG<P>::v;
+  A accg[G];
+  const int64_t o_base = rowblock * ((int64_t)RPB * G) + row_in_block;
+#pragma unroll
+  for (int g = 0; g < G; g++) accg[g] = P::identity();
+  const int64_t stepg = (int64_t)TPR * VEC;
+  for (int64_t r = (int64_t)tr * VEC; r < a.R; r += stepg) {
+    S v[G][VEC];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int64_t og = o_base + (int64_t)g * RPB;
+      if (og < a.O) {
+        int64_t ib, ob;
+        nxc_kept_offset(a.kept, og, a.small, ib, ob);
+        if (VEC > 1) nxc_load_vec<S, VEC>(in + ib + r, v[g]);
+        else v[g][0] = in[ib + r * a.s_inner];
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++)
+      if (o_base + (int64_t)g * RPB < a.O) {
+#pragma unroll
+        for (int j = 0; j < VEC; j++) P::step(accg[g], v[g][j], r + j);
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    A t = accg[g];
+    if (TPR <= 32) {
+      for (int m = TPR >> 1; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
+    } else {
+      for (int m = 16; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
+      __syncthreads();
+      sm[threadIdx.x] = t;
+      __syncthreads();
+      if (tr == 0) for (int w = 32; w < TPR; w += 32) t = P::combine(t, sm[threadIdx.x + w]);
+    }
+    const int64_t og = o_base + (int64_t)g * RPB;
+    if (og < a.O && tr == 0) {
+      int64_t ib, ob;
+      nxc_kept_offset(a.kept, og, a.small, ib, ob);
+      out[ob] = P::finish(t);
+    }
+  }
+}
+
 // ---- lane kernel -----------------------------------------------------------------
 template <class P, int VEC>
 __global__ void __launch_bounds__(NXC_FOLD_THREADS)
@@ -267,12 +292,13 @@ nxc_fold_lane_kernel(const typename P::S *__restrict__ in, typename P::SO *__res
     int64_t r = r0 + ty;
     if (a.red.n == 1) {
       const int64_t rs = a.red.in_stride[0];
-      for (; r + 3 * TY < r1; r += 4 * TY) {
-        S v[4][VEC];
+      constexpr int UL = NxcFoldG<P>::v;  // row loads in flight per thread
+      for (; r + (UL - 1) * TY < r1; r += UL * TY) {
+        S v[UL][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; u++) nxc_load_vec<S, VEC>(p + (r + u * TY) * rs, v[u]);
+        for (int u = 0; u < UL; u++) nxc_load_vec<S, VEC>(p + (r + u * TY) * rs, v[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < UL; u++)
 #pragma unroll
           for (int j = 0; j < VEC; j++) P::step(acc[j], v[u][j], r + u * TY);
       }
@@ -378,6 +404,18 @@ static inline void nxc_dimlist_set(NxcDimList &d, int n, const int64_t *shape, c
   }
 }
 
+// resident CTAs per SM of a kernel (queried once per instantiation): split reductions are sized
+// to exactly ONE wave of equal CTAs -- 1280 CTAs on 592 slots measured a third, 16 %-full wave
+template <class F>
+static inline int nxc_blocks_per_sm(F kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NXC_FOLD_THREADS, 0) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 4;
+  }
+  return n;
+}
+
 static inline int nxc_log2_ceil(int64_t x) {
   int l = 0;
   while (((int64_t)1 << l) < x) l++;
@@ -395,7 +433,8 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   const S *in = (const S *)p.in_base;
   SO *out = (SO *)p.out_base;
   const bool small = p.O < 0x7FFFFFFFLL && p.R < 0x7FFFFFFFLL && p.O * (double)p.R < 9.0e18;
-  const int64_t target_blocks = (int64_t)ctx->sm_count * 8;
+  static const int occ_row = nxc_blocks_per_sm(nxc_fold_row_kernel<P, VEC>);
+  static const int occ_lane = nxc_blocks_per_sm(nxc_fold_lane_kernel<P, VEC>);
 
   // lane candidate: kept dim with unit input stride and extent > 1
   int lane = -1;
@@ -436,9 +475,10 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
     const int64_t kother = p.O / a.C;
     const int64_t bx = a.lane_tiles * kother;
     int64_t S_ = 1;
+    const int64_t target_blocks = (int64_t)ctx->sm_count * occ_lane;
     if (bx < target_blocks) {
-      S_ = (target_blocks + bx - 1) / bx;
-      const int64_t max_s = (p.R + (int64_t)TY * 4 - 1) / ((int64_t)TY * 4);  // >= 4 rows per walker
+      S_ = target_blocks / bx;  // round down: one wave
+      const int64_t max_s = (p.R + (int64_t)TY * NxcFoldG<P>::v - 1) / ((int64_t)TY * NxcFoldG<P>::v);  // >= one unrolled pass per walker
       if (S_ > max_s) S_ = max_s;
       if (S_ > 1024) S_ = 1024;
       if (S_ < 1) S_ = 1;
@@ -497,11 +537,12 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   if (tl > 5 && items <= 512 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
-  a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * 4 * ctx->sm_count) ? 4 : 1;
+  a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * NxcFoldG<P>::v * ctx->sm_count) ? NxcFoldG<P>::v : 1;
   const int64_t rowblocks = (p.O + (int64_t)RPB * a.G - 1) / ((int64_t)RPB * a.G);
   int64_t S_ = 1;
+  const int64_t target_blocks = (int64_t)ctx->sm_count * occ_row;
   if (rowblocks < target_blocks && tl == 8) {
-    S_ = (target_blocks + rowblocks - 1) / rowblocks;
+    S_ = target_blocks / rowblocks;  // round down: one wave
     const int64_t per_pass = (int64_t)NXC_FOLD_THREADS * vec * 8;  // >= 8 vectors per thread
     const int64_t max_s = (p.R + per_pass - 1) / per_pass;
     if (S_ > max_s) S_ = max_s;
@@ -520,7 +561,10 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
     if (s) return s;
   }
   const int64_t grid = rowblocks * a.S;
-  if (vec > 1)
+  if (a.G > 1) {
+    if (vec > 1) nxc_fold_short_kernel<P, VEC><<<(unsigned)grid, NXC_FOLD_THREADS, 0, ctx->stream>>>(in, out, a);
+    else nxc_fold_short_kernel<P, 1><<<(unsigned)grid, NXC_FOLD_THREADS, 0, ctx->stream>>>(in, out, a);
+  } else if (vec > 1)
     nxc_fold_row_kernel<P, VEC><<<(unsigned)grid, NXC_FOLD_THREADS, 0, ctx->stream>>>(in, out, scr, a);
   else
     nxc_fold_row_kernel<P, 1><<<(unsigned)grid, NXC_FOLD_THREADS, 0, ctx->stream>>>(in, out, scr, a);

@@ -122,13 +122,15 @@ def sharded_reduce(x_local, op: str, axes, comm, backend=B):
 def sharded_argreduce(x_local, is_max: bool, axis: int, slab_offset: int, comm, backend=B):
     """argmax/argmin along `axis`; indices are global when axis == 0 is the sharded axis."""
     fn = backend.argmax if is_max else backend.argmin
-    idx = fn(x_local, axis, False)
     if axis != 0:
-        g = comm.allgather(idx)
+        g = comm.allgather(fn(x_local, axis, False))
         shp = tuple(g.shape)
         return backend.reshape(g, (shp[0] * shp[1],) + shp[2:]) if len(shp) >= 2 else g
-    val = backend.reduce(x_local, "max" if is_max else "min", [0])
-    # NaN-sticky max/min returns NaN exactly when the local argreduce picked a NaN: consistent
+    idxk = fn(x_local, 0, True)
+    idx = backend.reshape(idxk, tuple(idxk.shape[1:]))
+    # the local extreme is read back at the winning index (one element per output) instead of
+    # a second pass over the slab; it is NaN exactly when the local argreduce picked a NaN
+    val = backend.reshape(backend.gather(x_local, idxk, 0), tuple(idx.shape))
     gidx = backend.add(idx, backend.expand(backend.full(idx.context, D.int32, [], int(slab_offset)), idx.shape)
                        ) if len(idx.shape) else backend.add(idx, backend.full(idx.context, D.int32, [], int(slab_offset)))
     gv = comm.allgather(val)    # [world, ...]

@@ -30,6 +30,19 @@ def main(src, dst):
                     e[k] = {"value": float(d[k].replace(",", "")), "unit": u.get(k, "")}
                 except ValueError:
                     e[k] = {"value": d[k], "unit": u.get(k, "")}
+        # warp-stall breakdown: whatever this ncu version calls them, keep those that matter
+        for k in hdr:
+            if ("issue_stalled" in k and k.endswith(".pct")) or k in (
+                    "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
+                    "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct",
+                    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+                    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum"):
+                try:
+                    v = float(d[k].replace(",", ""))
+                except (ValueError, KeyError):
+                    continue
+                if "issue_stalled" not in k or v >= 4.0:
+                    e[k] = {"value": v, "unit": u.get(k, "")}
         rd, wr = e.get("dram__bytes_read.sum"), e.get("dram__bytes_write.sum")
         if rd and wr:
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
