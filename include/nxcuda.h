@@ -172,6 +172,24 @@ NXC_API nxc_status nxc_rfft(nxc_ctx *ctx, const nxc_tensor *out_complex, const n
 NXC_API nxc_status nxc_irfft(nxc_ctx *ctx, const nxc_tensor *out_real, const nxc_tensor *in_complex,
                              const int *axes, int n_axes, int64_t s_last);
 
+/* ---- linalg tier 1 ---------------------------------------------------------
+   replaces caml_nx_c_cholesky, caml_nx_c_triangular_solve (reference:
+   nx_c_tri.c:570-620) and caml_nx_c_qr (reference: nx_c_qr.c:421-433). Batched over
+   the leading dims, operands at arbitrary strides, outputs allocated by the binding
+   (cholesky / solve: the input / rhs shape; qr: reduced [m,k],[k,n] or full
+   [m,m],[m,n]). f16/bf16/fp8/f32 compute in f32; f64, c32, c64 natively; other
+   dtypes are Invalid_argument "linalg requires a float or complex dtype".
+   `flags` of the solve: bit 0 upper, bit 1 (conjugate) transpose, bit 2 unit
+   diagonal. Numeric failures are Failure "matrix is not positive definite" /
+   "triangular matrix is singular" (the OCaml veneer lifts them to Linalg_error,
+   backend_c/nx_backend.ml:582-594); the call reads one status word back, so these
+   three synchronise like the reference's do. */
+NXC_API nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int upper);
+NXC_API nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a,
+                                        const nxc_tensor *b, int flags);
+NXC_API nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r, const nxc_tensor *in,
+                          int reduced);
+
 /* ---- matmul ---------------------------------------------------------------
    replaces caml_nx_c_matmul (reference: nx_c_matmul.c:874-1108, 1271-1277).
    A [...,m,k] and B [...,k,n] at arbitrary strides with broadcast batch dims;

@@ -305,3 +305,122 @@ def irfft(x, dtype, axes, s=None):
             f[..., size - k] = np.conj(g[..., k])
     out = _dft_axis(f, f.ndim - 1, 1).real.astype(rt)
     return HostView.from_array(np.moveaxis(out, -1, last), dtype)
+
+
+# ---- linalg tier 1 --------------------------------------------------------------------------
+# Restated from the reference's UNBLOCKED kernels (nx_c_tri.c:30-52 cholesky diagonal block,
+# :108-139 la_trsm_unb; nx_c_qr.c:47-99 la_qr_panel, :133-163 la_qrq_unb) in numpy, in the compute
+# type the reference picks (f16/bf16/fp8/f32 -> f32; nx_c_linalg.h:183-200). The reference's
+# blocked paths (n above its block sizes) differ from these by rounding only.
+_LA_CT = {"f16": np.float32, "bf16": np.float32, "f8e4m3": np.float32, "f8e5m2": np.float32, "f32": np.float32,
+          "f64": np.float64, "c32": np.complex64, "c64": np.complex128}
+
+
+def _la_in(x, what):
+    if x.dtype not in _LA_CT:
+        raise RefError("Invalid_argument", "linalg requires a float or complex dtype")
+    if x.dtype in ("f16", "bf16", "f8e4m3", "f8e5m2"):
+        return cast(x, "f32").numpy().astype(np.float32)
+    return x.numpy().astype(_LA_CT[x.dtype])
+
+
+def _la_out(a, dtype):
+    if dtype in ("f16", "bf16", "f8e4m3", "f8e5m2"):
+        return cast(HostView.from_array(a.astype(np.float32), "f32"), dtype)
+    return HostView.from_array(a, dtype)
+
+
+def cholesky(x, upper=False):
+    if len(x.shape) < 2:
+        raise RefError("Invalid_argument", "operand shapes are incompatible")
+    if x.shape[-1] != x.shape[-2]:
+        raise RefError("Invalid_argument", "matrix must be square")
+    a = _la_in(x, "cholesky")
+    n = a.shape[-1]
+    out = np.zeros_like(a)
+    flat_in, flat_out = a.reshape((-1, n, n)), out.reshape((-1, n, n))
+    for b in range(flat_in.shape[0]):
+        A = flat_in[b].copy()
+        for j in range(n):
+            d = A[j, j].real - np.sum(np.abs(A[j, :j]) ** 2, dtype=A.real.dtype)
+            if not d > 0:
+                raise RefError("Failure", "matrix is not positive definite")
+            ljj = np.sqrt(d)
+            A[j, j] = ljj
+            for i in range(j + 1, n):
+                A[i, j] = (A[i, j] - np.dot(A[i, :j], np.conj(A[j, :j]))) / ljj
+        L = np.tril(A)
+        flat_out[b] = np.conj(L.T) if upper else L
+    return _la_out(out, x.dtype)
+
+
+def triangular_solve(a, b, upper=False, transpose=False, unit_diag=False):
+    vector_rhs = len(b.shape) == len(a.shape) - 1
+    if a.shape[-1] != a.shape[-2]:
+        raise RefError("Invalid_argument", "matrix must be square")
+    A = _la_in(a, "triangular_solve")
+    B = _la_in(b, "triangular_solve")
+    if vector_rhs:
+        B = B[..., None]
+    if A.shape[:-2] != B.shape[:-2] or B.shape[-2] != A.shape[-1]:
+        raise RefError("Invalid_argument", "operand shapes are incompatible")
+    n, nrhs = A.shape[-1], B.shape[-1]
+    X = B.copy()
+    fa, fx = A.reshape((-1, n, n)), X.reshape((-1, n, nrhs))
+    forward = bool(upper) == bool(transpose)
+    for bt in range(fa.shape[0]):
+        M = np.conj(fa[bt].T) if transpose else fa[bt]
+        for ii in range(n):
+            i = ii if forward else n - 1 - ii
+            diag = M[i, i]
+            if not unit_diag and diag == 0:
+                raise RefError("Failure", "triangular matrix is singular")
+            s = fx[bt, i].copy()
+            ks = range(0, i) if forward else range(i + 1, n)
+            for k in ks:
+                s = s - M[i, k] * fx[bt, k]
+            fx[bt, i] = s if unit_diag else s / diag
+    if vector_rhs:
+        X = X[..., 0]
+    return _la_out(X, b.dtype)
+
+
+def qr(x, reduced=True):
+    if len(x.shape) < 2:
+        raise RefError("Invalid_argument", "operand shapes are incompatible")
+    a = _la_in(x, "qr")
+    m, n = a.shape[-2], a.shape[-1]
+    k = min(m, n)
+    nq = k if reduced else m
+    fa = a.reshape((-1, m, n))
+    Qs = np.zeros((fa.shape[0], m, nq), dtype=a.dtype)
+    Rs = np.zeros((fa.shape[0], nq, n), dtype=a.dtype)
+    rt = a.real.dtype.type
+    for bt in range(fa.shape[0]):
+        A = fa[bt].copy()
+        tau = np.zeros(max(k, 1), dtype=a.dtype)
+        for j in range(k):
+            xnorm2 = rt(np.sum(np.abs(A[j + 1:, j]) ** 2, dtype=a.real.dtype))
+            alpha = A[j, j]
+            if xnorm2 == 0:
+                continue
+            anorm = np.sqrt(rt(abs(alpha) ** 2) + xnorm2)
+            beta = -anorm if alpha.real >= 0 else anorm
+            tau[j] = (beta - alpha.real) / beta - 1j * (alpha.imag / beta) if np.iscomplexobj(A) else (beta - alpha) / beta
+            A[j + 1:, j] = A[j + 1:, j] / (alpha - beta)
+            A[j, j] = beta
+            v = A[j + 1:, j]
+            w = np.conj(tau[j]) * (A[j, j + 1:] + np.conj(v) @ A[j + 1:, j + 1:])
+            A[j, j + 1:] -= w
+            A[j + 1:, j + 1:] -= np.outer(v, w)
+        Q = np.eye(m, nq, dtype=a.dtype)
+        for j in range(k - 1, -1, -1):
+            v = A[j + 1:, j]
+            w = tau[j] * (Q[j, :] + np.conj(v) @ Q[j + 1:, :])
+            Q[j, :] -= w
+            Q[j + 1:, :] -= np.outer(v, w)
+        Qs[bt] = Q
+        Rs[bt] = np.triu(A)[:nq, :]
+    qs, rs = list(a.shape), list(a.shape)
+    qs[-1], rs[-2] = nq, nq
+    return _la_out(Qs.reshape(qs), x.dtype), _la_out(Rs.reshape(rs), x.dtype)

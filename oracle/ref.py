@@ -310,4 +310,32 @@ def irfft(x, dtype, axes, s=None) -> HostView:
     return out
 
 
+# linalg tier 1: the binding owns the output shapes (reference: backend_c/nx_backend.ml:551-640)
+def cholesky(x, upper=False) -> HostView:
+    out = HostView.empty(x.dtype, x.shape)
+    call("cholesky", out, x, bool(upper))
+    return out
+
+
+def triangular_solve(a, b, upper=False, transpose=False, unit_diag=False) -> HostView:
+    vector_rhs = len(b.shape) == len(a.shape) - 1
+    bm = b.reshape_contig(list(b.shape) + [1]) if vector_rhs else b
+    out = HostView.empty(b.dtype, bm.shape)
+    call("triangular_solve", out, a, bm, (1 if upper else 0) | (2 if transpose else 0) | (4 if unit_diag else 0))
+    return out.reshape_contig(list(b.shape)) if vector_rhs else out
+
+
+def qr(x, reduced=True):
+    m, n = x.shape[-2], x.shape[-1]
+    k = min(m, n)
+    qs, rs = list(x.shape), list(x.shape)
+    if reduced:
+        qs[-1], rs[-2] = k, k
+    else:
+        qs[-1] = m
+    q, r = HostView.empty(x.dtype, qs), HostView.empty(x.dtype, rs)
+    call("qr", q, r, x, bool(reduced))
+    return q, r
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -70,6 +70,9 @@ SYMBOLS = {
     "nxc_argreduce": (_S, [_P, ctypes.c_int, _T, _T, ctypes.c_int]),
     "nxc_scan": (_S, [_P, ctypes.c_int, _T, _T, ctypes.c_int]),
     "nxc_matmul": (_S, [_P, _T, _T, _T]),
+    "nxc_cholesky": (_S, [_P, _T, _T, ctypes.c_int]),
+    "nxc_triangular_solve": (_S, [_P, _T, _T, _T, ctypes.c_int]),
+    "nxc_qr": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_fft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
     "nxc_rfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "nxc_irfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int64]),

@@ -614,3 +614,62 @@ def irfft(x: Tensor, dtype, axes, s=None) -> Tensor:
     _call(x.context, "irfft", x.context._lib.nxc_irfft, ctypes.byref(do), ctypes.byref(dx), ax, n,
           int(s[-1]) if s is not None else 0)
     return out
+
+
+# ---- linalg tier 1 (backend_c/nx_backend.ml:551-625) ---------------------------------------
+class LinalgError(Failure):
+    """`Backend_intf.Linalg_error {op; kind}` (backend_intf.ml:6-33): a numeric failure, lifted
+    from the engine's Failure text exactly as the reference veneer's `reraise_linalg` does."""
+
+    def __init__(self, op, kind, text):
+        super().__init__(text)
+        self.op, self.kind = op, kind
+
+
+def _reraise_linalg(op, fn):
+    try:
+        return fn()
+    except Failure as e:
+        msg = str(e)
+        for suffix, kind in (("matrix is not positive definite", "Not_positive_definite"),
+                             ("triangular matrix is singular", "Singular"),
+                             ("eigenvalue iteration did not converge", "No_convergence")):
+            if msg.endswith(suffix):
+                raise LinalgError(op, kind, msg) from None
+        raise
+
+
+def cholesky(x: Tensor, upper: bool = False) -> Tensor:
+    out = _create(x.context, x.dtype, x.shape)
+    do, dx = out._desc(), x._desc()
+    _reraise_linalg("cholesky", lambda: _call(x.context, "cholesky", x.context._lib.nxc_cholesky,
+                                              ctypes.byref(do), ctypes.byref(dx), 1 if upper else 0))
+    return out
+
+
+def triangular_solve(a: Tensor, b: Tensor, upper: bool = False, transpose: bool = False,
+                     unit_diag: bool = False) -> Tensor:
+    vector_rhs = len(b.shape) == len(a.shape) - 1
+    bm = reshape(b, tuple(b.shape) + (1,)) if vector_rhs else b
+    out = _create(b.context, b.dtype, bm.shape)
+    flags = (1 if upper else 0) | (2 if transpose else 0) | (4 if unit_diag else 0)
+    do, da, db = out._desc(), a._desc(), bm._desc()
+    _reraise_linalg("triangular_solve", lambda: _call(b.context, "triangular_solve", b.context._lib.nxc_triangular_solve,
+                                                      ctypes.byref(do), ctypes.byref(da), ctypes.byref(db), flags))
+    return reshape(out, b.shape) if vector_rhs else out
+
+
+def qr(x: Tensor, reduced: bool = True):
+    s = list(x.shape)
+    m, n = s[-2], s[-1]
+    k = m if m < n else n
+    qs, rs = list(s), list(s)
+    if reduced:
+        qs[-1], rs[-2] = k, k
+    else:
+        qs[-1] = m
+    q, r = _create(x.context, x.dtype, qs), _create(x.context, x.dtype, rs)
+    dq, dr, dx = q._desc(), r._desc(), x._desc()
+    _reraise_linalg("qr", lambda: _call(x.context, "qr", x.context._lib.nxc_qr, ctypes.byref(dq), ctypes.byref(dr),
+                                        ctypes.byref(dx), 1 if reduced else 0))
+    return q, r

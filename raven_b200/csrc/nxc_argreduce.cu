@@ -19,29 +19,64 @@ template <int IS_MAX, int DT> struct ArgP {
   typedef ArgAcc<C> A;
   static constexpr int cls = D::cls;
   static constexpr bool ok = (cls != NXC_CLS_COMPLEX);
-  // An accumulator that has taken nothing yet has idx < 0. Floats start from NaN so that the
-  // one-instruction "greater or unordered" test sends the first element (and any NaN) to the
-  // exact rule below; integers start from the weakest value, never take an equal element, and
-  // an output that ends with idx < 0 saw only that value: its answer is index 0 (finish).
+  // An accumulator that has taken nothing yet has idx < 0 and holds the weakest value (-inf /
+  // +inf, the type's lowest / highest): a strict comparison never takes an equal element, so an
+  // output that ends with idx < 0 saw nothing but that value and its answer is index 0 (finish).
   __device__ __forceinline__ static A identity() {
     A a;
     a.idx = -1;
-    if constexpr (cls == NXC_CLS_FLOAT) a.v = (C)NAN;
+    if constexpr (cls == NXC_CLS_FLOAT) a.v = IS_MAX ? (C)-INFINITY : (C)INFINITY;
     else if constexpr (cls == NXC_CLS_BOOL) a.v = IS_MAX ? (C)0 : (C)1;
     else a.v = IS_MAX ? std::numeric_limits<C>::lowest() : std::numeric_limits<C>::max();
     return a;
   }
-  // one element, visited in increasing index order per accumulator: a strict
-  // comparison keeps the first of equals, the NaN clause lets the first NaN win
+  // "v beats the accumulator": strictly better, or the first NaN (a NaN accumulator is stuck)
+  __device__ __forceinline__ static bool beats(C v, C accv) {
+    if constexpr (cls == NXC_CLS_FLOAT) return (IS_MAX ? !(v <= accv) : !(v >= accv)) && (accv == accv);
+    else return IS_MAX ? (v > accv) : (v < accv);
+  }
+  // one element, visited in increasing index order per accumulator
   __device__ __forceinline__ static void step(A &acc, S s, int64_t r) {
     const C v = D::ld(s);
-    if constexpr (cls == NXC_CLS_FLOAT) {
-      if (!(IS_MAX ? (v <= acc.v) : (v >= acc.v))) {  // v better, or v / acc NaN (acc NaN: empty or stuck)
-        const bool take = acc.idx < 0 || (IS_MAX ? (v > acc.v) : (v < acc.v)) || ((v != v) && !(acc.v != acc.v));
-        if (take) { acc.v = v; acc.idx = (int32_t)r; }
-      }
+    if (beats(v, acc.v)) { acc.v = v; acc.idx = (int32_t)r; }
+  }
+  // NaN-propagating extreme of two values
+  __device__ __forceinline__ static C better(C a, C b) {
+    if constexpr (cls == NXC_CLS_FLOAT && sizeof(C) == 4) {
+      float r;
+      if (IS_MAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+      else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+      return r;
+    } else if constexpr (cls == NXC_CLS_FLOAT) {
+      C r = (IS_MAX ? (b > a) : (b < a)) ? b : a;
+      return (b != b) ? b : r;
     } else {
-      if (IS_MAX ? (v > acc.v) : (v < acc.v)) { acc.v = v; acc.idx = (int32_t)r; }
+      return (IS_MAX ? (b > a) : (b < a)) ? b : a;
+    }
+  }
+  // N elements at indices r0, r0 + rs, ...: take the group's extreme first (N-1 instructions);
+  // only a group that beats the accumulator -- ever rarer as the walk proceeds -- pays for
+  // finding which element it was (the first NaN, else the first one equal to the extreme).
+  static constexpr bool MANY = true;
+  template <int N>
+  __device__ __forceinline__ static void step_many(A &acc, const S (&vals)[N], int64_t r0, int64_t rs) {
+    C c[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) c[i] = D::ld(vals[i]);
+    C m = c[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) m = better(m, c[i]);
+    if (beats(m, acc.v)) {
+      int sel = N - 1;
+#pragma unroll
+      for (int i = N - 2; i >= 0; i--) {
+        bool is;
+        if constexpr (cls == NXC_CLS_FLOAT) is = (m != m) ? (c[i] != c[i]) : (c[i] == m);
+        else is = c[i] == m;
+        if (is) sel = i;
+      }
+      acc.v = m;
+      acc.idx = (int32_t)(r0 + (int64_t)sel * rs);
     }
   }
   __device__ __forceinline__ static A combine(A a, A b) {

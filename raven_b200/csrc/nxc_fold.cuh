@@ -100,6 +100,21 @@ __device__ __forceinline__ A nxc_shfl_xor(const A &v, int mask) {
   return r.a;
 }
 
+// N elements whose reduced indices are r0, r0 + rs, ...: policies may fold them as a group
+// (argreduce takes the group's extreme first and touches its (value, index) pair only when the
+// group beats it); the default is the sequential per-element step.
+template <class P, class = void> struct NxcHasMany { static constexpr bool v = false; };
+template <class P> struct NxcHasMany<P, typename std::enable_if<P::MANY>::type> { static constexpr bool v = true; };
+template <class P, int N>
+__device__ __forceinline__ void nxc_step_many(typename P::A &acc, const typename P::S (&vals)[N], int64_t r0, int64_t rs) {
+  if constexpr (NxcHasMany<P>::v) {
+    P::template step_many<N>(acc, vals, r0, rs);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) P::step(acc, vals[i], r0 + i * rs);
+  }
+}
+
 // rows in flight per thread group on the short-row path: small accumulators afford 8
 template <class P> struct NxcFoldG { static constexpr int v = sizeof(typename P::A) <= 8 ? 8 : 4; };
 
@@ -155,16 +170,13 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
           else v[u][0] = p[(r + u * step) * a.s_inner];
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int j = 0; j < VEC; j++) P::step(acc[u], v[u][j], r + u * step + j);
+        for (int u = 0; u < 4; u++) nxc_step_many<P, VEC>(acc[u], v[u], r + u * step, 1);
       }
       for (; r < r1; r += step) {
         S v[VEC];
         if (VEC > 1) nxc_load_vec<S, VEC>(p + r, v);
         else v[0] = p[r * a.s_inner];
-#pragma unroll
-        for (int j = 0; j < VEC; j++) P::step(acc[0], v[j], r + j);
+        nxc_step_many<P, VEC>(acc[0], v, r, 1);
       }
     } else {
       for (; r < r1; r += step) {
@@ -177,8 +189,7 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
         S v[VEC];
         if (VEC > 1) nxc_load_vec<S, VEC>(p, v);
         else v[0] = p[0];
-#pragma unroll
-        for (int j = 0; j < VEC; j++) P::step(acc[0], v[j], r + j);
+        nxc_step_many<P, VEC>(acc[0], v, r, 1);
       }
     }
   }
@@ -201,45 +212,49 @@ nxc_fold_row_kernel(const typename P::S *__restrict__ in, typename P::SO *__rest
 }
 
 // ---- short-row kernel ---------------------------------------------------------------
+// Rows shorter than 256 work items, one kept dim (the usual [rows, R] case), no split: one
+// thread group of TPR lanes folds G rows at once (rows RPB apart), so G independent vector
+// loads are in flight per thread and iteration -- 128 bytes for the 4-byte types, what the
+// flat map kernel keeps in flight. Rows are a constant pointer step apart: no per-row decode.
 template <class P, int VEC>
 __global__ void __launch_bounds__(NXC_FOLD_THREADS)
 nxc_fold_short_kernel(const typename P::S *__restrict__ in, typename P::SO *__restrict__ out,
                       const __grid_constant__ NxcRowArgs a) {
   typedef typename P::S S;
   typedef typename P::A A;
+  constexpr int G = NxcFoldG<P>::v;
   __shared__ A sm[NXC_FOLD_THREADS];
   const int TPR = 1 << a.tpr_log2;
   const int RPB = NXC_FOLD_THREADS >> a.tpr_log2;
   const int tr = threadIdx.x & (TPR - 1);
-  const int row_in_block = threadIdx.x >> a.tpr_log2;
-  const int64_t rowblock = (int64_t)blockIdx.x;
-// Short rows (fewer than 256 work items per output, no split): one thread group folds G rows
-// at once (rows RPB apart), so G independent vector loads are in flight per thread and
-// iteration -- 128 bytes for the 4-byte types, what the flat map kernel keeps in flight.
-  constexpr int G = NxcFoldG<P>::v;
+  const int64_t o_base = (int64_t)blockIdx.x * ((int64_t)RPB * G) + (threadIdx.x >> a.tpr_log2);
+  const int64_t kin = a.kept.n ? a.kept.in_stride[0] : 0, kout = a.kept.n ? a.kept.out_stride[0] : 0;
+  // rows of this group that exist: g < n_live
+  int n_live = 0;
+  if (o_base < a.O) {
+    const int64_t left = (a.O - o_base + RPB - 1) / RPB;
+    n_live = left < G ? (int)left : G;
+  }
   A accg[G];
-  const int64_t o_base = rowblock * ((int64_t)RPB * G) + row_in_block;
 #pragma unroll
   for (int g = 0; g < G; g++) accg[g] = P::identity();
-  const int64_t stepg = (int64_t)TPR * VEC;
-  for (int64_t r = (int64_t)tr * VEC; r < a.R; r += stepg) {
+  const int step = TPR * VEC;
+  const int R = (int)a.R;
+  const int64_t gstep = (int64_t)RPB * kin;
+  const S *p = in + o_base * kin + (VEC > 1 ? (int64_t)tr * VEC : (int64_t)tr * a.s_inner);
+  const int64_t pstep = VEC > 1 ? (int64_t)step : (int64_t)step * a.s_inner;
+  for (int r = tr * VEC; r < R; r += step, p += pstep) {
     S v[G][VEC];
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      const int64_t og = o_base + (int64_t)g * RPB;
-      if (og < a.O) {
-        int64_t ib, ob;
-        nxc_kept_offset(a.kept, og, a.small, ib, ob);
-        if (VEC > 1) nxc_load_vec<S, VEC>(in + ib + r, v[g]);
-        else v[g][0] = in[ib + r * a.s_inner];
+      if (g < n_live) {
+        if (VEC > 1) nxc_load_vec<S, VEC>(p + g * gstep, v[g]);
+        else v[g][0] = p[g * gstep];
       }
     }
 #pragma unroll
     for (int g = 0; g < G; g++)
-      if (o_base + (int64_t)g * RPB < a.O) {
-#pragma unroll
-        for (int j = 0; j < VEC; j++) P::step(accg[g], v[g][j], r + j);
-      }
+      if (g < n_live) nxc_step_many<P, VEC>(accg[g], v[g], r, 1);
   }
 #pragma unroll
   for (int g = 0; g < G; g++) {
@@ -253,12 +268,7 @@ nxc_fold_short_kernel(const typename P::S *__restrict__ in, typename P::SO *__re
       __syncthreads();
       if (tr == 0) for (int w = 32; w < TPR; w += 32) t = P::combine(t, sm[threadIdx.x + w]);
     }
-    const int64_t og = o_base + (int64_t)g * RPB;
-    if (og < a.O && tr == 0) {
-      int64_t ib, ob;
-      nxc_kept_offset(a.kept, og, a.small, ib, ob);
-      out[ob] = P::finish(t);
-    }
+    if (g < n_live && tr == 0) out[(o_base + (int64_t)g * RPB) * kout] = P::finish(t);
   }
 }
 
@@ -298,9 +308,12 @@ nxc_fold_lane_kernel(const typename P::S *__restrict__ in, typename P::SO *__res
 #pragma unroll
         for (int u = 0; u < UL; u++) nxc_load_vec<S, VEC>(p + (r + u * TY) * rs, v[u]);
 #pragma unroll
-        for (int u = 0; u < UL; u++)
+        for (int j = 0; j < VEC; j++) {
+          S col[UL];
 #pragma unroll
-          for (int j = 0; j < VEC; j++) P::step(acc[j], v[u][j], r + u * TY);
+          for (int u = 0; u < UL; u++) col[u] = v[u][j];
+          nxc_step_many<P, UL>(acc[j], col, r, TY);
+        }
       }
       for (; r < r1; r += TY) {
         S v[VEC];
@@ -537,7 +550,7 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   if (tl > 5 && items <= 512 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
-  a.G = (tl < 8 && p.nr <= 1 && p.O >= (int64_t)RPB * NxcFoldG<P>::v * ctx->sm_count) ? NxcFoldG<P>::v : 1;
+  a.G = (tl < 8 && p.nr <= 1 && p.nk <= 1 && p.R < 0x7FFFFFFFLL && p.O >= (int64_t)RPB * NxcFoldG<P>::v * ctx->sm_count) ? NxcFoldG<P>::v : 1;
   const int64_t rowblocks = (p.O + (int64_t)RPB * a.G - 1) / ((int64_t)RPB * a.G);
   int64_t S_ = 1;
   const int64_t target_blocks = (int64_t)ctx->sm_count * occ_row;

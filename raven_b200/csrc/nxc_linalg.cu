@@ -1,0 +1,408 @@
+// nxc_linalg.cu -- linalg tier 1: cholesky, triangular_solve, qr.
+// Replaces caml_nx_c_cholesky / caml_nx_c_triangular_solve (reference: nx_c_tri.c:570-620, drivers
+// :296-566) and caml_nx_c_qr (reference: nx_c_qr.c:421-433, driver :321-418).
+//
+// Contract kept from the reference: compute type per storage dtype (f16/bf16/fp8/f32 -> f32, f64,
+// c32, c64; anything else is Invalid_argument "linalg requires a float or complex dtype",
+// nx_c_linalg.h:183-200); batched over the leading dims, operands at arbitrary strides; cholesky
+// reads the LOWER triangle only, fails with "matrix is not positive definite" on a pivot that is
+// not > 0 (NaN included) and writes zeros in the other triangle, ~upper returns L^H;
+// triangular_solve's `transpose` is the CONJUGATE transpose, an exactly-zero pivot (non-unit
+// diagonal) is "triangular matrix is singular"; qr is Householder with LAPACK's pivot sign
+// (beta = -sign(re alpha) * norm), tau = 0 for a column already zero below the diagonal, Q formed
+// by applying the reflectors to the identity in reverse order, reduced or full shapes.
+//
+// How: operands are brought into contiguous compute-type work matrices by the backend's own
+// cast / copy kernels (any strides, any storage dtype), ONE CTA per batch matrix then runs the
+// factorization with the matrix in global memory (L2-resident at these sizes): right-looking
+// rank-1 updates for cholesky and the substitution (parallel over the trailing block, coalesced
+// along rows), one thread per column for the Householder applies -- the reference's unblocked
+// operation order, so small matrices agree to rounding. Results go back through cast / copy.
+// A device status word reports numeric failure; the host reads it (one 4-byte read-back) because
+// the reference raises synchronously. Large single matrices want the blocked, GEMM-fed variant;
+// this one is sized for the batched small/medium factorizations ML code issues.
+#include "nxc_ops.cuh"
+
+#define NXC_LA_THREADS 512
+
+static const char NXC_LA_NOT_PD[] = "matrix is not positive definite";
+static const char NXC_LA_SINGULAR[] = "triangular matrix is singular";
+static const char NXC_LA_NOT_FLOAT[] = "linalg requires a float or complex dtype";
+static const char NXC_LA_NOT_SQUARE[] = "matrix must be square";
+static const char NXC_LA_SHAPE[] = "operand shapes are incompatible";
+
+// ---- scalar algebra over the four compute types ------------------------------------------------
+template <class T> struct LA;
+template <> struct LA<float> {
+  typedef float R;
+  __device__ static float conj(float a) { return a; }
+  __device__ static float norm2(float a) { return a * a; }
+  __device__ static float real(float a) { return a; }
+  __device__ static float imag(float) { return 0.f; }
+  __device__ static float mk(float re, float) { return re; }
+  __device__ static float add(float a, float b) { return a + b; }
+  __device__ static float sub(float a, float b) { return a - b; }
+  __device__ static float mul(float a, float b) { return a * b; }
+  __device__ static float div(float a, float b) { return a / b; }
+  __device__ static float divr(float a, float r) { return a / r; }
+  __device__ static bool is_zero(float a) { return a == 0.f; }
+  __device__ static float rsqrt_(float a) { return sqrtf(a); }
+};
+template <> struct LA<double> {
+  typedef double R;
+  __device__ static double conj(double a) { return a; }
+  __device__ static double norm2(double a) { return a * a; }
+  __device__ static double real(double a) { return a; }
+  __device__ static double imag(double) { return 0.0; }
+  __device__ static double mk(double re, double) { return re; }
+  __device__ static double add(double a, double b) { return a + b; }
+  __device__ static double sub(double a, double b) { return a - b; }
+  __device__ static double mul(double a, double b) { return a * b; }
+  __device__ static double div(double a, double b) { return a / b; }
+  __device__ static double divr(double a, double r) { return a / r; }
+  __device__ static bool is_zero(double a) { return a == 0.0; }
+  __device__ static double rsqrt_(double a) { return sqrt(a); }
+};
+template <class Z, class R_> struct LAZ {
+  typedef R_ R;
+  __device__ static Z conj(Z a) { return zmk<Z>(a.re, -a.im); }
+  __device__ static R norm2(Z a) { return a.re * a.re + a.im * a.im; }
+  __device__ static R real(Z a) { return a.re; }
+  __device__ static R imag(Z a) { return a.im; }
+  __device__ static Z mk(R re, R im) { return zmk<Z>(re, im); }
+  __device__ static Z add(Z a, Z b) { return zadd(a, b); }
+  __device__ static Z sub(Z a, Z b) { return zsub(a, b); }
+  __device__ static Z mul(Z a, Z b) { return zmk<Z>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+  __device__ static Z div(Z a, Z b) { return zdiv(a, b); }
+  __device__ static Z divr(Z a, R r) { return zmk<Z>(a.re / r, a.im / r); }
+  __device__ static bool is_zero(Z a) { return a.re == (R)0 && a.im == (R)0; }
+};
+template <> struct LA<cf32> : LAZ<cf32, float> { __device__ static float rsqrt_(float a) { return sqrtf(a); } };
+template <> struct LA<cf64> : LAZ<cf64, double> { __device__ static double rsqrt_(double a) { return sqrt(a); } };
+
+// CTA-wide sum of one real per thread (result broadcast to every thread)
+template <class R>
+__device__ R nxc_la_block_sum(R v, R *sm) {
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  R t = (R)0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sm[w];
+  return t;
+}
+
+// ---- cholesky: A = L L^H, lower, right-looking, in place on an n x n row-major work matrix -----
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_cholesky_kernel(T *work, int64_t n, int upper, int *status) {
+  typedef LA<T> L;
+  typedef typename L::R R;
+  T *A = work + (int64_t)blockIdx.x * n * n;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int64_t j = 0; j < n; j++) {
+    // pivot: every earlier column's update has already been subtracted from A[j][j]
+    if (threadIdx.x == 0) {
+      const R d = L::real(A[j * n + j]);
+      if (!(d > (R)0)) { bad = 1; atomicExch(status, 1); }
+      else A[j * n + j] = L::mk(L::rsqrt_(d), (R)0);
+    }
+    __syncthreads();
+    if (bad) return;
+    const R ljj = L::real(A[j * n + j]);
+    for (int64_t i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i * n + j] = L::divr(A[i * n + j], ljj);
+    __syncthreads();
+    // trailing lower triangle: A[i][c] -= L[i][j] * conj(L[c][j]),  j < c <= i
+    const int64_t t = n - 1 - j;
+    for (int64_t e = threadIdx.x; e < t * t; e += blockDim.x) {
+      const int64_t i = j + 1 + e / t, c = j + 1 + e % t;
+      if (c <= i) A[i * n + c] = L::sub(A[i * n + c], L::mul(A[i * n + j], L::conj(A[c * n + j])));
+    }
+    __syncthreads();
+  }
+  // the other triangle: zeros for ~lower; ~upper returns L^H and zeros below
+  for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int64_t i = e / n, c = e % n;
+    if (c > i) A[i * n + c] = upper ? L::conj(A[c * n + i]) : L::mk((R)0, (R)0);
+  }
+  if (upper) {
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int64_t i = e / n, c = e % n;
+      if (c < i) A[i * n + c] = L::mk((R)0, (R)0);
+    }
+  }
+}
+
+// ---- triangular solve: op(A) X = B in place on X (n x nrhs), A n x n ----------------------------
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_trsm_kernel(const T *aw, T *xw, int64_t n, int64_t nrhs, int upper, int transpose, int unit, int *status) {
+  typedef LA<T> L;
+  const T *A = aw + (int64_t)blockIdx.x * n * n;
+  T *X = xw + (int64_t)blockIdx.x * n * nrhs;
+  const bool forward = (upper != 0) == (transpose != 0);
+  for (int64_t ii = 0; ii < n; ii++) {
+    const int64_t i = forward ? ii : n - 1 - ii;
+    const T diag = transpose ? L::conj(A[i * n + i]) : A[i * n + i];
+    if (!unit && L::is_zero(diag)) {  // uniform across the CTA
+      if (threadIdx.x == 0) atomicExch(status, 2);
+      return;
+    }
+    if (!unit) {
+      for (int64_t j = threadIdx.x; j < nrhs; j += blockDim.x) X[i * nrhs + j] = L::div(X[i * nrhs + j], diag);
+      __syncthreads();
+    }
+    // rows not yet solved lose their coupling to row i
+    const int64_t rest = n - 1 - ii;
+    for (int64_t e = threadIdx.x; e < rest * nrhs; e += blockDim.x) {
+      const int64_t q = e / nrhs, j = e - q * nrhs;
+      const int64_t r = forward ? i + 1 + q : i - 1 - q;
+      const T c = transpose ? L::conj(A[i * n + r]) : A[r * n + i];
+      X[r * nrhs + j] = L::sub(X[r * nrhs + j], L::mul(c, X[i * nrhs + j]));
+    }
+    __syncthreads();
+  }
+}
+
+// ---- Householder QR on an m x n work matrix; Q (m x nq) formed from the reflectors ----------------
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_qr_kernel(T *work, T *qbuf, T *taubuf, int64_t m, int64_t n, int64_t nq) {
+  typedef LA<T> L;
+  typedef typename L::R R;
+  T *A = work + (int64_t)blockIdx.x * m * n;
+  T *Q = qbuf + (int64_t)blockIdx.x * m * nq;
+  const int64_t k = m < n ? m : n;
+  T *tau = taubuf + (int64_t)blockIdx.x * (k > 0 ? k : 1);
+  __shared__ R red[NXC_LA_THREADS / 32];
+  __shared__ T s_tau;
+  for (int64_t j = 0; j < k; j++) {
+    R part = (R)0;
+    for (int64_t i = j + 1 + threadIdx.x; i < m; i += blockDim.x) part += L::norm2(A[i * n + j]);
+    const R xnorm2 = nxc_la_block_sum<R>(part, red);
+    const T alpha = A[j * n + j];
+    const R alphr = L::real(alpha);
+    if (xnorm2 == (R)0) {  // uniform
+      if (threadIdx.x == 0) tau[j] = L::mk((R)0, (R)0);
+      __syncthreads();
+      continue;
+    }
+    const R anorm = L::rsqrt_(L::norm2(alpha) + xnorm2);
+    const R beta = alphr >= (R)0 ? -anorm : anorm;
+    const T tj = L::mk((beta - alphr) / beta, -L::imag(alpha) / beta);
+    const T scal = L::sub(alpha, L::mk(beta, (R)0));
+    __syncthreads();  // everyone has read alpha
+    for (int64_t i = j + 1 + threadIdx.x; i < m; i += blockDim.x) A[i * n + j] = L::div(A[i * n + j], scal);
+    if (threadIdx.x == 0) { A[j * n + j] = L::mk(beta, (R)0); tau[j] = tj; s_tau = tj; }
+    __syncthreads();
+    // apply H_j^H to the columns right of j: one thread per column, rows in order
+    const T tauc = L::conj(s_tau);
+    for (int64_t c = j + 1 + threadIdx.x; c < n; c += blockDim.x) {
+      T w = A[j * n + c];
+      for (int64_t i = j + 1; i < m; i++) w = L::add(w, L::mul(L::conj(A[i * n + j]), A[i * n + c]));
+      w = L::mul(tauc, w);
+      A[j * n + c] = L::sub(A[j * n + c], w);
+      for (int64_t i = j + 1; i < m; i++) A[i * n + c] = L::sub(A[i * n + c], L::mul(w, A[i * n + j]));
+    }
+    __syncthreads();
+  }
+  // Q = H_0 ... H_{k-1} applied to the identity, last reflector first
+  for (int64_t e = threadIdx.x; e < m * nq; e += blockDim.x) {
+    const int64_t i = e / nq, c = e - i * nq;
+    Q[e] = i == c ? L::mk((R)1, (R)0) : L::mk((R)0, (R)0);
+  }
+  __syncthreads();
+  for (int64_t jj = 0; jj < k; jj++) {
+    const int64_t j = k - 1 - jj;
+    const T tj = tau[j];
+    for (int64_t c = threadIdx.x; c < nq; c += blockDim.x) {
+      T w = Q[j * nq + c];
+      for (int64_t i = j + 1; i < m; i++) w = L::add(w, L::mul(L::conj(A[i * n + j]), Q[i * nq + c]));
+      w = L::mul(tj, w);
+      Q[j * nq + c] = L::sub(Q[j * nq + c], w);
+      for (int64_t i = j + 1; i < m; i++) Q[i * nq + c] = L::sub(Q[i * nq + c], L::mul(w, A[i * n + j]));
+    }
+    __syncthreads();
+  }
+  // R: the upper trapezoid; the reflector tails below the diagonal become zeros
+  for (int64_t e = threadIdx.x; e < m * n; e += blockDim.x) {
+    const int64_t i = e / n, c = e - i * n;
+    if (c < i) A[e] = L::mk((R)0, (R)0);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int nxc_la_compute_dtype(int dt) {
+  switch (dt) {
+    case NXC_F16: case NXC_BF16: case NXC_F8E4M3: case NXC_F8E5M2: case NXC_F32: return NXC_F32;
+    case NXC_F64: return NXC_F64;
+    case NXC_C32: return NXC_C32;
+    case NXC_C64: return NXC_C64;
+    default: return -1;
+  }
+}
+
+// contiguous [batch..., rows, cols] descriptor over a fresh work buffer
+static nxc_status nxc_la_work(nxc_ctx *ctx, const nxc_tensor *like, int cdt, int64_t rows, int64_t cols, nxc_tensor *w,
+                              void **buf) {
+  *w = *like;
+  w->dtype = cdt;
+  w->offset = 0;
+  w->shape[w->ndim - 2] = rows;
+  w->shape[w->ndim - 1] = cols;
+  int64_t st = 1;
+  for (int d = w->ndim - 1; d >= 0; d--) { w->strides[d] = st; st *= w->shape[d]; }
+  nxc_status s = nxc_alloc(ctx, (size_t)(st > 0 ? st : 1) * (size_t)nxc_elem_size(cdt), buf);
+  w->data = *buf;
+  return s;
+}
+
+// storage -> work (cast when the dtypes differ, else copy); work -> storage likewise
+static nxc_status nxc_la_move(nxc_ctx *ctx, const nxc_tensor *dst, const nxc_tensor *src) {
+  return dst->dtype == src->dtype ? nxc_copy(ctx, dst, src) : nxc_cast(ctx, dst, src);
+}
+
+static nxc_status nxc_la_status(nxc_ctx *ctx, int *dev_status) {
+  int h = 0;
+  NXC_CUDA_TRY(ctx, cudaMemcpyAsync(&h, dev_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h == 1) return NXC_LA_NOT_PD;
+  if (h == 2) return NXC_LA_SINGULAR;
+  return NXC_OK;
+}
+
+static nxc_status nxc_la_fail(nxc_ctx *ctx, nxc_status s) {
+  if (s && strcmp(s, NXC_ERR_CUDA) != 0) snprintf(ctx->err, sizeof ctx->err, "%s", s);
+  return s;
+}
+
+#define NXC_LA_DISPATCH(cdt, ...)                                         \
+  switch (cdt) {                                                          \
+    case NXC_F32: { typedef float T; __VA_ARGS__ } break;                 \
+    case NXC_F64: { typedef double T; __VA_ARGS__ } break;                \
+    case NXC_C32: { typedef cf32 T; __VA_ARGS__ } break;                  \
+    default: { typedef cf64 T; __VA_ARGS__ } break;                       \
+  }
+
+extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int upper) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_la_fail(ctx, s);
+  if (in->ndim < 2 || out->ndim != in->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t n = in->shape[in->ndim - 1];
+  if (in->shape[in->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_NOT_SQUARE);
+  if (out->shape[out->ndim - 1] != n || out->shape[out->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int cdt = nxc_la_compute_dtype(in->dtype);
+  if (cdt < 0) return nxc_la_fail(ctx, NXC_LA_NOT_FLOAT);
+  int64_t nbatch = 1;
+  for (int i = 0; i < in->ndim - 2; i++) {
+    if (out->shape[i] != in->shape[i]) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= in->shape[i];
+  }
+  if (n == 0 || nbatch == 0) return NXC_OK;
+  nxc_tensor w;
+  void *buf = NULL;
+  int *st = NULL;
+  if ((s = nxc_la_work(ctx, in, cdt, n, n, &w, &buf))) return nxc_la_fail(ctx, s);
+  s = nxc_alloc(ctx, sizeof(int), (void **)&st);
+  if (!s) s = nxc_memset(ctx, st, 0, sizeof(int));
+  if (!s) s = nxc_la_move(ctx, &w, in);
+  if (!s) {
+    NXC_LA_DISPATCH(cdt, { nxc_cholesky_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)buf, n, upper, st); })
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "cholesky");
+  }
+  if (!s) s = nxc_la_status(ctx, st);
+  // the reference leaves a failed matrix unwritten and still writes the others; a failed call's
+  // output is unspecified either way, so nothing is written back on failure
+  if (!s) s = nxc_la_move(ctx, out, &w);
+  nxc_free(ctx, buf);
+  if (st) nxc_free(ctx, st);
+  return nxc_la_fail(ctx, s);
+}
+
+extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a, const nxc_tensor *b,
+                                           int flags) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(a)) || (s = nxc_check_tensor(b)) || (s = nxc_check_tensor(out))) return nxc_la_fail(ctx, s);
+  if (a->ndim < 2 || b->ndim != a->ndim || out->ndim != b->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t n = a->shape[a->ndim - 1];
+  if (a->shape[a->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_NOT_SQUARE);
+  const int64_t nrhs = b->shape[b->ndim - 1];
+  if (b->shape[b->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  if (out->shape[out->ndim - 2] != n || out->shape[out->ndim - 1] != nrhs) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int cdt = nxc_la_compute_dtype(a->dtype);
+  if (cdt < 0) return nxc_la_fail(ctx, NXC_LA_NOT_FLOAT);
+  if (b->dtype != a->dtype || out->dtype != a->dtype) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  int64_t nbatch = 1;
+  for (int i = 0; i < a->ndim - 2; i++) {
+    if (b->shape[i] != a->shape[i] || out->shape[i] != a->shape[i]) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= a->shape[i];
+  }
+  if (n == 0 || nrhs == 0 || nbatch == 0) return NXC_OK;
+  nxc_tensor aw, xw;
+  void *abuf = NULL, *xbuf = NULL;
+  int *st = NULL;
+  if ((s = nxc_la_work(ctx, a, cdt, n, n, &aw, &abuf))) return nxc_la_fail(ctx, s);
+  s = nxc_la_work(ctx, b, cdt, n, nrhs, &xw, &xbuf);
+  if (!s) s = nxc_alloc(ctx, sizeof(int), (void **)&st);
+  if (!s) s = nxc_memset(ctx, st, 0, sizeof(int));
+  if (!s) s = nxc_la_move(ctx, &aw, a);
+  if (!s) s = nxc_la_move(ctx, &xw, b);
+  if (!s) {
+    NXC_LA_DISPATCH(cdt, {
+      nxc_trsm_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((const T *)abuf, (T *)xbuf, n, nrhs, flags & 1,
+                                                                               (flags >> 1) & 1, (flags >> 2) & 1, st);
+    })
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "triangular_solve");
+  }
+  if (!s) s = nxc_la_status(ctx, st);
+  if (!s) s = nxc_la_move(ctx, out, &xw);
+  nxc_free(ctx, abuf);
+  if (xbuf) nxc_free(ctx, xbuf);
+  if (st) nxc_free(ctx, st);
+  return nxc_la_fail(ctx, s);
+}
+
+extern "C" nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r, const nxc_tensor *in, int reduced) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(q)) || (s = nxc_check_tensor(r))) return nxc_la_fail(ctx, s);
+  if (in->ndim < 2 || q->ndim != in->ndim || r->ndim != in->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t m = in->shape[in->ndim - 2], n = in->shape[in->ndim - 1];
+  const int64_t k = m < n ? m : n;
+  const int64_t nq = reduced ? k : m;
+  if (q->shape[q->ndim - 2] != m || q->shape[q->ndim - 1] != nq) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  if (r->shape[r->ndim - 2] != nq || r->shape[r->ndim - 1] != n) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int cdt = nxc_la_compute_dtype(in->dtype);
+  if (cdt < 0) return nxc_la_fail(ctx, NXC_LA_NOT_FLOAT);
+  int64_t nbatch = 1;
+  for (int i = 0; i < in->ndim - 2; i++) {
+    if (q->shape[i] != in->shape[i] || r->shape[i] != in->shape[i]) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= in->shape[i];
+  }
+  if (nbatch == 0 || m == 0) return NXC_OK;
+  nxc_tensor w, qw;
+  void *wbuf = NULL, *qbuf = NULL, *tbuf = NULL;
+  if ((s = nxc_la_work(ctx, in, cdt, m, n, &w, &wbuf))) return nxc_la_fail(ctx, s);
+  s = nxc_la_work(ctx, in, cdt, m, nq, &qw, &qbuf);
+  if (!s) s = nxc_alloc(ctx, (size_t)nbatch * (size_t)(k > 0 ? k : 1) * (size_t)nxc_elem_size(cdt), &tbuf);
+  if (!s && n > 0) s = nxc_la_move(ctx, &w, in);
+  if (!s) {
+    NXC_LA_DISPATCH(cdt, { nxc_qr_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)wbuf, (T *)qbuf, (T *)tbuf, m, n, nq); })
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr");
+  }
+  if (!s && nq > 0) s = nxc_la_move(ctx, q, &qw);
+  if (!s && nq > 0 && n > 0) {
+    // R = the first nq rows of the work matrix (its lower part already zeroed)
+    nxc_tensor rv = w;
+    rv.shape[rv.ndim - 2] = nq;
+    s = nxc_la_move(ctx, r, &rv);
+  }
+  nxc_free(ctx, wbuf);
+  if (qbuf) nxc_free(ctx, qbuf);
+  if (tbuf) nxc_free(ctx, tbuf);
+  return nxc_la_fail(ctx, s);
+}

@@ -263,69 +263,69 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
   const uint32_t rb = nxc_fastdiv(blockIdx.x, args.chunks_div);
   const uint32_t chunk = blockIdx.x - rb * args.chunks;
   S1 va[U][VW]; S2 vb[U][VW]; S3 vc[U][VW];
+  const bool ba = args.bcast_mask & 2u, bb = args.bcast_mask & 4u, bc = args.bcast_mask & 8u;
+  const bool na = args.neg_mask & 2u, nb = args.neg_mask & 4u, nc = args.neg_mask & 8u;
+  // the 4 slots of a thread are a constant pointer step apart (TX items along the row, or TY
+  // rows): pointers advance by addition, and "slot u exists" is u < n_live
+  S0 *po; const S1 *pa; const S2 *pb; const S3 *pc;
+  int64_t so, sa, sb, sc;
+  int n_live;
   if (!ROWS) {
     const int64_t row = (int64_t)rb * TY + ty;
-    if (row >= args.rows) return;
     const int64_t in0 = (int64_t)chunk * (TX * U) + tx;
+    if (row >= args.rows || in0 >= args.ni) return;
     int64_t off[NOP];
     nxc_row_offsets<NOP, NOP>(args, row, off);
-    S0 *po = out + off[0] + in0 * args.inner_stride[0];
-    const S1 *pa = a + off[KA] + in0 * args.inner_stride[KA];
-    const S2 *pb = b + off[KB] + in0 * args.inner_stride[KB];
-    const S3 *pc = c + off[KC] + in0 * args.inner_stride[KC];
+    po = out + off[0] + in0 * args.inner_stride[0];
+    pa = a + off[KA] + in0 * args.inner_stride[KA];
+    pb = b + off[KB] + in0 * args.inner_stride[KB];
+    pc = c + off[KC] + in0 * args.inner_stride[KC];
+    so = (int64_t)TX * args.inner_stride[0]; sa = (int64_t)TX * args.inner_stride[KA];
+    sb = (int64_t)TX * args.inner_stride[KB]; sc = (int64_t)TX * args.inner_stride[KC];
+    const int64_t left = (args.ni - in0 + TX - 1) >> args.tx_log2;
+    n_live = left < U ? (int)left : U;
+  } else if (args.ndim <= 1) {
+    const int64_t item = (int64_t)chunk * TX + tx;
+    const int64_t row0 = (int64_t)rb * (TY * U) + ty;
+    if (item >= args.ni || row0 >= args.rows) return;
+    const int64_t r0 = args.ndim ? args.stride[0][0] : 0, ra = args.ndim ? args.stride[KA][0] : 0,
+                  rb_ = args.ndim ? args.stride[KB][0] : 0, rc = args.ndim ? args.stride[KC][0] : 0;
+    po = out + row0 * r0 + item * args.inner_stride[0];
+    pa = a + row0 * ra + item * args.inner_stride[KA];
+    pb = b + row0 * rb_ + item * args.inner_stride[KB];
+    pc = c + row0 * rc + item * args.inner_stride[KC];
+    so = (int64_t)TY * r0; sa = (int64_t)TY * ra; sb = (int64_t)TY * rb_; sc = (int64_t)TY * rc;
+    const int64_t left = (args.rows - row0 + TY - 1) / TY;
+    n_live = left < U ? (int)left : U;
+  } else {
+    n_live = -1;
+  }
+  if (!ROWS || n_live >= 0) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      if (in0 + (int64_t)u * TX < args.ni) {
-        const int64_t d = (int64_t)(u * TX);
-        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa + d * args.inner_stride[KA], args.bcast_mask & 2u, args.neg_mask & 2u, va[u]);
-        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb + d * args.inner_stride[KB], args.bcast_mask & 4u, args.neg_mask & 4u, vb[u]);
-        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc + d * args.inner_stride[KC], args.bcast_mask & 8u, args.neg_mask & 8u, vc[u]);
+      if (u < n_live) {
+        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, ba, na, va[u]);
+        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, bb, nb, vb[u]);
+        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, bc, nc, vc[u]);
       }
+      pa += sa; pb += sb; pc += sc;
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      if (in0 + (int64_t)u * TX < args.ni) {
+      if (u < n_live) {
         S0 vo[VW];
 #pragma unroll
         for (int i = 0; i < VW; i++) vo[i] = K::run(va[u][i], vb[u][i], vc[u][i], prm);
-        S0 *q = po + (int64_t)(u * TX) * args.inner_stride[0];
-        if (VW == 1) q[0] = vo[0];
-        else nxc_store_vec<S0, VW>(q, vo);
+        if (VW == 1) po[0] = vo[0];
+        else nxc_store_vec<S0, VW>(po, vo);
       }
+      po += so;
     }
   } else {
     const int64_t item = (int64_t)chunk * TX + tx;
     if (item >= args.ni) return;
     const int64_t row0 = (int64_t)rb * (TY * U) + ty;
-    if (args.ndim <= 1) {
-      // one outer dim: rows TY apart are a constant pointer step apart
-      const int64_t s0 = args.ndim ? args.stride[0][0] : 0, sa = args.ndim ? args.stride[KA][0] : 0,
-                    sb = args.ndim ? args.stride[KB][0] : 0, sc = args.ndim ? args.stride[KC][0] : 0;
-      S0 *po = out + row0 * s0 + item * args.inner_stride[0];
-      const S1 *pa = a + row0 * sa + item * args.inner_stride[KA];
-      const S2 *pb = b + row0 * sb + item * args.inner_stride[KB];
-      const S3 *pc = c + row0 * sc + item * args.inner_stride[KC];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (row0 + (int64_t)(u * TY) < args.rows) {
-          const int64_t d = (int64_t)(u * TY);
-          if (K::NIN >= 1) nxc_load_item<S1, VW>(pa + d * sa, args.bcast_mask & 2u, args.neg_mask & 2u, va[u]);
-          if (K::NIN >= 2) nxc_load_item<S2, VW>(pb + d * sb, args.bcast_mask & 4u, args.neg_mask & 4u, vb[u]);
-          if (K::NIN >= 3) nxc_load_item<S3, VW>(pc + d * sc, args.bcast_mask & 8u, args.neg_mask & 8u, vc[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (row0 + (int64_t)(u * TY) < args.rows) {
-          S0 vo[VW];
-#pragma unroll
-          for (int i = 0; i < VW; i++) vo[i] = K::run(va[u][i], vb[u][i], vc[u][i], prm);
-          S0 *q = po + (int64_t)(u * TY) * s0;
-          if (VW == 1) q[0] = vo[0];
-          else nxc_store_vec<S0, VW>(q, vo);
-        }
-      }
-    } else {
+    {
       // several outer dims: coordinates are decoded per row, one row at a time
 #pragma unroll 1
       for (int u = 0; u < U; u++) {

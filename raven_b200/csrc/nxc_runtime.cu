@@ -158,7 +158,10 @@ extern "C" int nxc_status_is_invalid_argument(nxc_status s) {
   if (!s) return 0;
   static const char *inv[] = {NXC_ERR_EMPTY_REDUCE, NXC_ERR_AXES, NXC_ERR_AXIS,
                               NXC_ERR_OUT_RANK, NXC_ERR_OUT_ALIASED, NXC_ERR_SHAPE,
-                              "threefry: last axis must have extent 2"};
+                              "threefry: last axis must have extent 2",
+                              // linalg preconditions (reference: la_raise, nx_c_linalg.h:310-318)
+                              "linalg requires a float or complex dtype", "matrix must be square",
+                              "operand shapes are incompatible"};
   for (size_t i = 0; i < sizeof inv / sizeof inv[0]; i++)
     if (strcmp(s, inv[i]) == 0) return 1;
   return 0;

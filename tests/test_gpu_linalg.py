@@ -1,0 +1,129 @@
+"""GPU parity of linalg tier 1 against the oracle through the C
+ABI: cholesky (lower / upper), triangular_solve (upper x conjugate-transpose x unit-diagonal,
+matrix and vector right-hand sides), qr (reduced / full, tall / wide / square), batched, every
+float / complex dtype the reference accepts (f16 / bf16 compute in f32), strided operands, the
+reference's failure classes. Tolerances are relative to the largest output magnitude; larger
+single matrices are checked through residuals (A = L L^H, op(A) X = B, A = Q R, Q^H Q = I).
+"""
+import numpy as np
+import pytest
+
+import raven_b200.backend as B
+from raven_b200 import Failure, InvalidArgument
+from tests import harness as H
+from tests.golden.make_golden_linalg import WIDE, _mk, hv_of
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 4e-4, "f64": 1e-11, "c32": 4e-4, "c64": 1e-11, "bf16": 6e-2, "f16": 8e-3}
+DTS = ["f32", "f64", "c32", "c64", "bf16", "f16"]
+
+
+def _wide(oracle, hv):
+    return oracle.cast(hv, WIDE[hv.dtype]).numpy()
+
+
+def _dev_wide(oracle, t, dt):
+    arr = H.download(t)
+    return _wide(oracle, H.HostView.from_array(arr, dt) if arr.dtype != np.uint16 else H.HostView(arr.reshape(-1), dt, list(arr.shape)))
+
+
+def _close(got, want, dt, what, scale=1.0):
+    assert got.shape == want.shape, what
+    if want.size:
+        err = np.abs(got - want).max() / max(1.0, np.abs(want).max())
+        assert err <= TOL[dt] * scale, f"{what}: {err:.3e}"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_cholesky_and_solve(ctx, oracle, dt):
+    rng = np.random.default_rng(41)
+    for bshape, n in (((), 1), ((), 4), ((2,), 7), ((2, 3), 5), ((), 40)):
+        a = _mk(rng, bshape + (n, n), dt)
+        spd = hv_of(a @ np.conj(np.swapaxes(a, -1, -2)) + n * np.eye(n), dt)
+        for upper in (False, True):
+            want = _wide(oracle, oracle.cholesky(spd, upper))
+            got = _dev_wide(oracle, B.cholesky(H.upload(ctx, spd), upper), dt)
+            _close(got, want, dt, f"cholesky/{dt}/{bshape}/{n}/upper={upper}")
+        tri = {False: hv_of(np.tril(a) / n + np.eye(n), dt), True: hv_of(np.triu(a) / n + np.eye(n), dt)}
+        for nrhs in (1, 3):
+            b = hv_of(_mk(rng, bshape + (n, nrhs), dt), dt)
+            for upper, tr, unit in ((False, False, False), (False, True, False), (True, False, True),
+                                    (True, True, False), (False, False, True)):
+                want = _wide(oracle, oracle.triangular_solve(tri[upper], b, upper, tr, unit))
+                got = _dev_wide(oracle, B.triangular_solve(H.upload(ctx, tri[upper]), H.upload(ctx, b), upper, tr, unit), dt)
+                _close(got, want, dt, f"trsm/{dt}/{bshape}/{n}/{nrhs}/{upper}{tr}{unit}", scale=4)
+        # vector right-hand side (rank one less than A)
+        bv = hv_of(_mk(rng, bshape + (n,), dt), dt)
+        want = _wide(oracle, oracle.triangular_solve(tri[False], bv, False, False, False))
+        got = _dev_wide(oracle, B.triangular_solve(H.upload(ctx, tri[False]), H.upload(ctx, bv)), dt)
+        _close(got, want, dt, f"trsm-vector/{dt}/{bshape}/{n}", scale=4)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_qr(ctx, oracle, dt):
+    rng = np.random.default_rng(42)
+    for bshape, m, n in (((), 4, 4), ((2,), 6, 3), ((), 3, 6), ((2,), 1, 1), ((), 30, 20), ((3,), 8, 8)):
+        x = hv_of(_mk(rng, bshape + (m, n), dt), dt)
+        for red in (True, False):
+            wq, wr = oracle.qr(x, red)
+            gq, gr = B.qr(H.upload(ctx, x), red)
+            _close(_dev_wide(oracle, gq, dt), _wide(oracle, wq), dt, f"qr.Q/{dt}/{bshape}/{m}x{n}/{red}", scale=4)
+            _close(_dev_wide(oracle, gr, dt), _wide(oracle, wr), dt, f"qr.R/{dt}/{bshape}/{m}x{n}/{red}", scale=4)
+
+
+def test_linalg_strided_operands(ctx, oracle):
+    rng = np.random.default_rng(43)
+    n = 6
+    a = rng.standard_normal((n, n))
+    spd = H.HostView.from_array(a @ a.T + n * np.eye(n), "f64")
+    for name, v in {"T": spd.permute([1, 0]), "flip": spd.flip([True, True])}.items():
+        want = oracle.cholesky(v, False).numpy()
+        got = H.download(B.cholesky(H.upload(ctx, v), False))
+        _close(got, want, "f64", f"cholesky/strided/{name}")
+    x = H.HostView.from_array(rng.standard_normal((5, 8)), "f64").permute([1, 0])
+    wq, wr = oracle.qr(x, True)
+    gq, gr = B.qr(H.upload(ctx, x), True)
+    _close(H.download(gq), wq.numpy(), "f64", "qr/strided/Q", scale=4)
+    _close(H.download(gr), wr.numpy(), "f64", "qr/strided/R", scale=4)
+
+
+def test_linalg_residuals_large(ctx):
+    """Sizes beyond what the oracle checks quickly: residual properties in f64."""
+    rng = np.random.default_rng(44)
+    n = 300
+    a = rng.standard_normal((2, n, n))
+    spd = a @ np.swapaxes(a, -1, -2) + n * np.eye(n)
+    L = H.download(B.cholesky(H.upload(ctx, H.HostView.from_array(spd, "f64"))))
+    assert np.abs(L @ np.swapaxes(L, -1, -2) - spd).max() <= 1e-10 * np.abs(spd).max()
+    assert np.abs(np.triu(L[0], 1)).max() == 0.0
+    b = rng.standard_normal((2, n, 5))
+    X = H.download(B.triangular_solve(H.upload(ctx, H.HostView.from_array(L, "f64")), H.upload(ctx, H.HostView.from_array(b, "f64"))))
+    assert np.abs(L @ X - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+    m = rng.standard_normal((200, 120))
+    q, r = B.qr(H.upload(ctx, H.HostView.from_array(m, "f64")), True)
+    q, r = H.download(q), H.download(r)
+    assert np.abs(q @ r - m).max() <= 1e-11 * n
+    assert np.abs(q.T @ q - np.eye(120)).max() <= 1e-12 * n
+    assert np.abs(np.tril(r, -1)).max() == 0.0
+
+
+def test_linalg_errors(ctx):
+    up = lambda a, dt: H.upload(ctx, H.HostView.from_array(a, dt))
+    with pytest.raises(Failure, match="cholesky: matrix is not positive definite") as e:
+        B.cholesky(up(-np.eye(3), "f64"))
+    assert isinstance(e.value, B.LinalgError) and e.value.kind == "Not_positive_definite"
+    with pytest.raises(Failure, match="cholesky: matrix is not positive definite"):
+        B.cholesky(up(np.full((2, 2), np.nan), "f32"))
+    with pytest.raises(InvalidArgument, match="cholesky: matrix must be square"):
+        B.cholesky(up(np.ones((2, 3)), "f64"))
+    with pytest.raises(InvalidArgument, match="cholesky: linalg requires a float or complex dtype"):
+        B.cholesky(up(np.ones((2, 2), dtype=np.int32), "i32"))
+    with pytest.raises(Failure, match="triangular_solve: triangular matrix is singular") as e:
+        B.triangular_solve(up(np.zeros((3, 3)), "f64"), up(np.ones((3, 2)), "f64"))
+    assert e.value.kind == "Singular"
+    with pytest.raises(InvalidArgument, match="triangular_solve: operand shapes are incompatible"):
+        B.triangular_solve(up(np.eye(3), "f64"), up(np.ones((4, 2)), "f64"))
+    # a unit-diagonal solve never looks at the (zero) diagonal
+    x = H.download(B.triangular_solve(up(np.zeros((3, 3)), "f64"), up(np.ones((3, 2)), "f64"), unit_diag=True))
+    assert np.array_equal(x, np.ones((3, 2)))
