@@ -266,11 +266,48 @@ let irfft ?s x ~dtype ~axes =
   caml_irfft out x axes (match s with Some sizes -> sizes | None -> [||]);
   out
 
+(* ---- linalg tier 1 (backend_c/nx_backend.ml:551-625). Numeric failures arrive as
+   [Failure "<op>: <reason>"] and are lifted to [Linalg_error] by suffix, like the reference's
+   [reraise_linalg]; the three booleans of the solve travel as one int (bit 0 upper, 1 transpose,
+   2 unit diagonal). ---- *)
+external caml_cholesky : ('a, 'b) t -> ('a, 'b) t -> bool -> unit = "nx_cuda_cholesky"
+external caml_trsm : ('a, 'b) t -> ('a, 'b) t -> ('a, 'b) t -> int -> unit = "nx_cuda_triangular_solve"
+external caml_qr : ('a, 'b) t -> ('a, 'b) t -> ('a, 'b) t -> bool -> unit = "nx_cuda_qr"
+
+let lift_linalg ~op f =
+  try f () with Failure msg as e ->
+    let kind =
+      if String.ends_with ~suffix:"matrix is not positive definite" msg then Some `Not_positive_definite
+      else if String.ends_with ~suffix:"triangular matrix is singular" msg then Some `Singular
+      else if String.ends_with ~suffix:"eigenvalue iteration did not converge" msg then Some `No_convergence
+      else None in
+    (match kind with Some kind -> raise (Backend_intf.Linalg_error { op; kind }) | None -> raise e)
+
+let cholesky ~upper x =
+  let out = create_tensor x.context x.dtype x.shape in
+  lift_linalg ~op:"cholesky" (fun () -> caml_cholesky out x upper);
+  out
+
+let triangular_solve ~upper ~transpose ~unit_diag a b =
+  let vec = Array.length b.shape = Array.length a.shape - 1 in
+  let bm = if vec then reshape b (Array.append b.shape [| 1 |]) else b in
+  let out = create_tensor b.context b.dtype bm.shape in
+  let flags = Bool.to_int upper lor (Bool.to_int transpose lsl 1) lor (Bool.to_int unit_diag lsl 2) in
+  lift_linalg ~op:"triangular_solve" (fun () -> caml_trsm out a bm flags);
+  if vec then reshape out b.shape else out
+
+let qr ~reduced x =
+  let nd = Array.length x.shape in
+  let m = x.shape.(nd - 2) and n = x.shape.(nd - 1) in
+  let k = Int.min m n in
+  let qs = Array.copy x.shape and rs = Array.copy x.shape in
+  if reduced then (qs.(nd - 1) <- k; rs.(nd - 2) <- k) else qs.(nd - 1) <- m;
+  let q = create_tensor x.context x.dtype qs and r = create_tensor x.context x.dtype rs in
+  lift_linalg ~op:"qr" (fun () -> caml_qr q r x reduced);
+  (q, r)
+
 (* ---- not yet behind the C ABI (scope table 8f rank 4): fail loudly, never fall back ---- *)
 let todo op = failwith (op ^ ": not implemented by nx-cuda")
-let cholesky ~upper:_ _ = todo "cholesky"
-let triangular_solve ~upper:_ ~transpose:_ ~unit_diag:_ _ _ = todo "triangular_solve"
-let qr ~reduced:_ _ = todo "qr"
 let svd ~full_matrices:_ _ = todo "svd"
 let eigvals _ = todo "eigvals"
 let eig _ = todo "eig"

@@ -307,3 +307,27 @@ CAMLprim value nx_cuda_irfft(value vout, value vin, value vaxes, value vs) {
   if (s) raise_status("irfft", CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
+
+/* ---- linalg tier 1 (replaces caml_nx_c_cholesky / _triangular_solve, nx_c_tri.c:570-620, and
+   caml_nx_c_qr, nx_c_qr.c:421-433) ---- */
+CAMLprim value nx_cuda_cholesky(value vout, value vin, value vupper) {
+  CAMLparam3(vout, vin, vupper);
+  nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
+  nxc_status s = nxc_cholesky(CTX_OF(vout), &o, &a, Bool_val(vupper));
+  if (s) raise_status("cholesky", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_triangular_solve(value vout, value va, value vb, value vflags) {
+  CAMLparam4(vout, va, vb, vflags);
+  nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
+  nxc_status s = nxc_triangular_solve(CTX_OF(vout), &o, &a, &b, Int_val(vflags));
+  if (s) raise_status("triangular_solve", CTX_OF(vout), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_qr(value vq, value vr, value vin, value vreduced) {
+  CAMLparam4(vq, vr, vin, vreduced);
+  nxc_tensor q, r, a; tensor_of_value(vq, &q); tensor_of_value(vr, &r); tensor_of_value(vin, &a);
+  nxc_status s = nxc_qr(CTX_OF(vq), &q, &r, &a, Bool_val(vreduced));
+  if (s) raise_status("qr", CTX_OF(vq), s);
+  CAMLreturn(Val_unit);
+}
