@@ -313,6 +313,22 @@ def main():
         t_ms = k0.elapsed_time(k1) / 10
         per_op[name] = {"ms": round(t_ms, 4), "gbs": round(nbytes / (t_ms * 1e-3) / 1e9, 1),
                         "frac": round(nbytes / (t_ms * 1e-3) / 1e9 / pk["hbm"], 4)}
+    if comm is not None:
+        # the sharded forms of the four reductions (local kernel + exchange), same protocol
+        for name, fn, nbytes in [("sharded_sum_all", lambda: sharded.sharded_reduce(a, "sum", [0], comm), 4 * n),
+                                 ("sharded_sum_axis0", lambda: sharded.sharded_reduce(A, "sum", [0], comm), 4 * n),
+                                 ("sharded_sum_axis1", lambda: sharded.sharded_reduce(A, "sum", [1], comm), 4 * n),
+                                 ("sharded_argmax", lambda: sharded.sharded_argreduce(a, True, 0, rank * n, comm), 4 * n)]:
+            fn()
+            sync_all()
+            k0.record(stream)
+            for _ in range(10):
+                fn()
+            k1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = k0.elapsed_time(k1) / 10
+            per_op[name] = {"ms": round(t_ms, 4), "gbs": round(nbytes / (t_ms * 1e-3) / 1e9, 1),
+                            "frac": round(nbytes / (t_ms * 1e-3) / 1e9 / pk["hbm"], 4)}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_add.json")
     if os.path.exists(tpath):
@@ -350,6 +366,10 @@ def main():
             matmul = {"error": str(e)}
 
     # ---- end to end: host buffers in, host results out --------------------------------------
+    # the clock sampler covers the device-timed regions above and stops here: nvidia-smi polling
+    # takes driver locks the copy engines' submissions wait on (measured: the same pipelined step
+    # ran 47 ms without the poller and 75-185 ms with it)
+    clocks = sampler.stop() if sampler else None
     del out
     nbytes = 4 * n
     # pinned host buffers: inputs go up through the upload engine, the elementwise result comes
@@ -385,7 +405,6 @@ def main():
     e2e = {"value": round(world * step_bytes(n) / e2e_s / 1e9, 2), "unit": "GB/s",
            "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3),
            "steps": e2e_steps}
-    clocks = sampler.stop() if sampler else None
     # the last step's read-back is complete (sync_all above drains the device): check it
     if not np.array_equal(pr[:1024], (pa[:1024] + pb[:1024])):
         raise SystemExit("e2e: read-back of add(a, b) does not match the host inputs")

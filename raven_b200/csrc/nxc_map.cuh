@@ -196,22 +196,20 @@ nxc_map_flat_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__re
 // coordinates once (32-bit multiply-shift division per outer dim) and then only adds multiples
 // of the inner stride, so there is no per-element division; all 4 items' loads are issued
 // before any result is computed.
-// one operand's work item: VW elements forwards, backwards (reversed in registers) or one
-// broadcast element
+// one operand's work item: VW elements (forwards, or the VW elements ending at p for a reversed
+// run) or one broadcast element in r[0]. Nothing here CONSUMES a loaded value: a register move
+// after the load would make the thread wait for that load before issuing the next slot's (ncu:
+// 72 % of the stall samples sat on the broadcast moves) -- nxc_item_elem picks the element at
+// compute time instead.
 template <typename S, int VW>
 __device__ __forceinline__ void nxc_load_item(const S *p, bool bcast, bool neg, S (&r)[VW]) {
-  if (VW == 1 || bcast) {
-    const S s = *p;
-#pragma unroll
-    for (int i = 0; i < VW; i++) r[i] = s;
-  } else if (neg) {
-    S t[VW];
-    nxc_load_vec<S, VW>(p - (VW - 1), t);
-#pragma unroll
-    for (int i = 0; i < VW; i++) r[i] = t[VW - 1 - i];
-  } else {
-    nxc_load_vec<S, VW>(p, r);
-  }
+  if (VW == 1 || bcast) r[0] = *p;
+  else nxc_load_vec<S, VW>(neg ? p - (VW - 1) : p, r);
+}
+template <typename S, int VW>
+__device__ __forceinline__ S nxc_item_elem(const S (&r)[VW], int i, bool bcast, bool neg) {
+  if (VW == 1) return r[0];
+  return bcast ? r[0] : (neg ? r[VW - 1 - i] : r[i]);
 }
 
 // row -> element offsets of the first NEED operands (the outer coordinates' contribution)
@@ -315,7 +313,9 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
       if (u < n_live) {
         S0 vo[VW];
 #pragma unroll
-        for (int i = 0; i < VW; i++) vo[i] = K::run(va[u][i], vb[u][i], vc[u][i], prm);
+        for (int i = 0; i < VW; i++)
+          vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], i, bb, nb),
+                         nxc_item_elem<S3, VW>(vc[u], i, bc, nc), prm);
         if (VW == 1) po[0] = vo[0];
         else nxc_store_vec<S0, VW>(po, vo);
       }
@@ -338,7 +338,9 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
         if (K::NIN >= 3) nxc_load_item<S3, VW>(c + off[KC] + item * args.inner_stride[KC], args.bcast_mask & 8u, args.neg_mask & 8u, vc[0]);
         S0 vo[VW];
 #pragma unroll
-        for (int i = 0; i < VW; i++) vo[i] = K::run(va[0][i], vb[0][i], vc[0][i], prm);
+        for (int i = 0; i < VW; i++)
+          vo[i] = K::run(nxc_item_elem<S1, VW>(va[0], i, ba, na), nxc_item_elem<S2, VW>(vb[0], i, bb, nb),
+                         nxc_item_elem<S3, VW>(vc[0], i, bc, nc), prm);
         S0 *q = out + off[0] + item * args.inner_stride[0];
         if (VW == 1) q[0] = vo[0];
         else nxc_store_vec<S0, VW>(q, vo);

@@ -71,12 +71,24 @@ def step():
     return got
 
 
-step()
-drain()
-t0 = time.perf_counter()
-for _ in range(5):
+def pipelined():
     step()
-drain()
-out["pipelined_step_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 2)
+    drain()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step()
+    drain()
+    return round((time.perf_counter() - t0) / 5 * 1e3, 2)
+
+
+out["pipelined_step_ms"] = pipelined()
+# the same with an nvidia-smi poller running beside it (what bench.py's clock sampler does)
+import subprocess  # noqa: E402
+poller = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms",
+                           "100", "-i", "0"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+time.sleep(0.5)
+out["pipelined_step_ms_with_nvidia_smi_poller"] = pipelined()
+poller.terminate()
+poller.wait()
 out["copy_engines"] = os.environ.get("NX_CUDA_COPY_ENGINES", "1")
 print(json.dumps(out))
