@@ -366,9 +366,7 @@ def main():
             matmul = {"error": str(e)}
 
     # ---- end to end: host buffers in, host results out --------------------------------------
-    # the clock sampler covers the device-timed regions above and stops here: nvidia-smi polling
-    # takes driver locks the copy engines' submissions wait on (measured: the same pipelined step
-    # ran 47 ms without the poller and 75-185 ms with it)
+    # the clock sampler covers the device-timed regions above and stops here
     clocks = sampler.stop() if sampler else None
     del out
     nbytes = 4 * n
@@ -381,6 +379,7 @@ def main():
 
     def e2e_step():
         nonlocal a, b, A
+        a = b = A = None   # release the previous step's inputs before allocating this step's
         a = B.from_host(ctx, pa)
         b = B.from_host(ctx, pb)
         A = B.reshape(a, [rows_local, side])
@@ -390,7 +389,12 @@ def main():
         return got
 
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    # W untimed steps first, like the device-timed loop: the first pipelined steps grow the
+    # stream-ordered pool (a read-back still owns its buffer when the next step allocates), and a
+    # pool growth of 1 GiB costs 100+ ms of driver time -- measured 46 ms/step once warm against
+    # 75-185 ms when those growths landed in a 5-step timed region after a single warm-up step
+    for _ in range(args.warmup):
+        e2e_step()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -402,6 +406,35 @@ def main():
         td.all_reduce(t, op=td.ReduceOp.MAX)
         e2e_s = float(t.item())
     d2h = nbytes + sum(int(x.nbytes) for x in res)
+    if os.environ.get("NX_BENCH_E2E_DEBUG") == "1" and rank == 0:
+        # where one step's wall time goes, each phase drained before the next starts
+        def _t(fn):
+            t1 = time.perf_counter()
+            r = fn()
+            ctx.sync()
+            torch.cuda.synchronize()
+            return r, round((time.perf_counter() - t1) * 1e3, 2)
+        (ua, ub), t_up = _t(lambda: (B.from_host(ctx, pa), B.from_host(ctx, pb)))
+        a, b = ua, ub
+        A = B.reshape(a, [rows_local, side])
+        outs, t_ops = _t(step)
+        _, t_small = _t(lambda: [B.to_host(x) for x in outs[3:]])
+        _, t_back = _t(lambda: B.to_host_async(outs[0], pr))
+        sys.stderr.write(f"e2e debug: upload {t_up} ms, ops {t_ops} ms, small read-backs {t_small} ms, "
+                         f"1 GiB read-back {t_back} ms\n")
+        each = {}
+        for nm, fn in (("add", lambda: B.add(a, b)), ("mul", lambda: B.mul(a, b)), ("sin", lambda: B.sin(a)),
+                       ("sum", lambda: B.reduce(a, "sum", [0])), ("sum0", lambda: B.reduce(A, "sum", [0])),
+                       ("sum1", lambda: B.reduce(A, "sum", [1])), ("argmax", lambda: B.argmax(a, 0)),
+                       ("add again", lambda: B.add(a, b)), ("step again", step)):
+            t1 = time.perf_counter()
+            r = fn()
+            t_call = time.perf_counter() - t1
+            ctx.sync()
+            torch.cuda.synchronize()
+            each[nm] = (round(t_call * 1e3, 2), round((time.perf_counter() - t1) * 1e3, 2))
+            del r
+        sys.stderr.write(f"e2e debug per op (call ms, call+drain ms): {each}\n")
     e2e = {"value": round(world * step_bytes(n) / e2e_s / 1e9, 2), "unit": "GB/s",
            "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3),
            "steps": e2e_steps}

@@ -189,6 +189,13 @@ NXC_API nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, con
                                         const nxc_tensor *b, int flags);
 NXC_API nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r, const nxc_tensor *in,
                           int reduced);
+/* eigh / eigvalsh (linalg tier 2): replaces caml_nx_c_eigh (reference: nx_c_eigh.c; veneer
+   backend_c/nx_backend.ml:627-648). Reads the LOWER triangle of the Hermitian input; `w_f64`
+   ([batch..., n], always float64) receives the eigenvalues in ascending order; `v` (input dtype
+   and shape, columns = eigenvectors) is written only when vectors != 0 (pass the input there
+   otherwise, as the reference veneer does). Failure "eigenvalue iteration did not converge". */
+NXC_API nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w_f64, const nxc_tensor *v, const nxc_tensor *in,
+                            int vectors);
 
 /* ---- matmul ---------------------------------------------------------------
    replaces caml_nx_c_matmul (reference: nx_c_matmul.c:874-1108, 1271-1277).
@@ -208,6 +215,11 @@ NXC_API nxc_status nxc_cat(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor
                    int axis);
 NXC_API nxc_status nxc_gather(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
                       const nxc_tensor *indices_i32, int axis);
+/* nxc_gather for indices the backend produced itself (argmax / argmin / argsort results): the
+   range flag is not read back, so the call does not drain the stream. Out-of-range indices
+   are still never dereferenced. */
+NXC_API nxc_status nxc_gather_trusted(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
+                                      const nxc_tensor *indices_i32, int axis);
 /* `out` is pre-seeded with the template; mode 0 = Set (last write wins), 1 = Add. */
 NXC_API nxc_status nxc_scatter(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *indices_i32,
                        const nxc_tensor *updates, int axis, int mode);

@@ -338,4 +338,37 @@ def qr(x, reduced=True):
     return q, r
 
 
+# linalg tiers 2-3 (reference: backend_c/nx_backend.ml:627-720): eigenvalues / singular values
+# are always f64, eig's outputs always c64
+def eigh(x, vectors=True):
+    w = HostView.empty("f64", list(x.shape[:-2]) + [x.shape[-1]])
+    if not vectors:
+        call("eigh", w, x, x, False)
+        return w
+    v = HostView.empty(x.dtype, x.shape)
+    call("eigh", w, v, x, True)
+    return w, v
+
+
+def svd(x, full_matrices=False):
+    m, n = x.shape[-2], x.shape[-1]
+    k = min(m, n)
+    batch = list(x.shape[:-2])
+    u = HostView.empty(x.dtype, batch + ([m, m] if full_matrices else [m, k]))
+    sv = HostView.empty("f64", batch + [k])
+    vt = HostView.empty(x.dtype, batch + ([n, n] if full_matrices else [k, n]))
+    call("svd", u, sv, vt, x)
+    return u, sv, vt
+
+
+def eig(x, vectors=True):
+    w = HostView.empty("c64", list(x.shape[:-2]) + [x.shape[-1]])
+    if not vectors:
+        call("eig", w, w, x, False)
+        return w
+    v = HostView.empty("c64", x.shape)
+    call("eig", w, v, x, True)
+    return w, v
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -73,12 +73,14 @@ SYMBOLS = {
     "nxc_cholesky": (_S, [_P, _T, _T, ctypes.c_int]),
     "nxc_triangular_solve": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_qr": (_S, [_P, _T, _T, _T, ctypes.c_int]),
+    "nxc_eigh": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_fft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
     "nxc_rfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "nxc_irfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int64]),
     "nxc_pad": (_S, [_P, _T, _T, _P, ctypes.POINTER(ctypes.c_int64)]),
     "nxc_cat": (_S, [_P, _T, ctypes.POINTER(_T), ctypes.c_int, ctypes.c_int]),
     "nxc_gather": (_S, [_P, _T, _T, _T, ctypes.c_int]),
+    "nxc_gather_trusted": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_scatter": (_S, [_P, _T, _T, _T, ctypes.c_int, ctypes.c_int]),
     "nxc_threefry": (_S, [_P, _T, _T, _T]),
     "nxc_unfold": (_S, [_P, _T, _T, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int64)] * 4),

@@ -418,11 +418,13 @@ def cat(tensors, axis: int) -> Tensor:
     return out
 
 
-def gather(data: Tensor, indices: Tensor, axis: int) -> Tensor:
+def gather(data: Tensor, indices: Tensor, axis: int, trusted: bool = False) -> Tensor:
+    """`trusted`: the indices come from the backend's own argmax / argmin / argsort, so the
+    out-of-range flag is not read back and the call does not drain the stream."""
     out = _create(data.context, data.dtype, indices.shape)
     do, dd, di = out._desc(), data._desc(), indices._desc()
-    _call(data.context, "gather", data.context._lib.nxc_gather, ctypes.byref(do), ctypes.byref(dd),
-          ctypes.byref(di), axis)
+    fn = data.context._lib.nxc_gather_trusted if trusted else data.context._lib.nxc_gather
+    _call(data.context, "gather", fn, ctypes.byref(do), ctypes.byref(dd), ctypes.byref(di), axis)
     return out
 
 
@@ -673,3 +675,25 @@ def qr(x: Tensor, reduced: bool = True):
     _reraise_linalg("qr", lambda: _call(x.context, "qr", x.context._lib.nxc_qr, ctypes.byref(dq), ctypes.byref(dr),
                                         ctypes.byref(dx), 1 if reduced else 0))
     return q, r
+
+
+# ---- linalg tier 2: eigh / eigvalsh (backend_c/nx_backend.ml:627-648) ------------------------
+def _eigh_values(x: Tensor) -> Tensor:
+    return _create(x.context, _dt.float64, tuple(x.shape[:-2]) + (x.shape[-1],))
+
+
+def eigvalsh(x: Tensor) -> Tensor:
+    w = _eigh_values(x)
+    dw, dx = w._desc(), x._desc()
+    _reraise_linalg("eigvalsh", lambda: _call(x.context, "eigvalsh", x.context._lib.nxc_eigh, ctypes.byref(dw),
+                                              ctypes.byref(dx), ctypes.byref(dx), 0))
+    return w
+
+
+def eigh(x: Tensor):
+    w = _eigh_values(x)
+    v = _create(x.context, x.dtype, x.shape)
+    dw, dv, dx = w._desc(), v._desc(), x._desc()
+    _reraise_linalg("eigh", lambda: _call(x.context, "eigh", x.context._lib.nxc_eigh, ctypes.byref(dw),
+                                          ctypes.byref(dv), ctypes.byref(dx), 1))
+    return w, v

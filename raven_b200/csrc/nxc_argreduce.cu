@@ -89,6 +89,26 @@ template <int IS_MAX, int DT> struct ArgP {
     acc.v = hit ? m : acc.v;
     acc.idx = hit ? i0 + sel * is : acc.idx;
   }
+  // The lanes of one thread group (a power of two <= 32, `mask` their lane mask) hold partials of
+  // the same output: the group's extreme by a NaN-propagating butterfly on the VALUE alone, then
+  // the lowest index among the lanes that hold it (REDUX.MIN) -- ~15 instructions instead of
+  // log2(lanes) merges of (value, index) pairs.
+  static constexpr bool WARP = true;
+  __device__ __forceinline__ static A warp_combine(A t, int lanes, unsigned mask) {
+    C m = t.v;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+      if (s < lanes) m = better(m, nxc_shfl_xor(m, s));
+    bool mine;
+    if constexpr (cls == NXC_CLS_FLOAT) mine = (m != m) ? (t.v != t.v) : (t.v == m);
+    else mine = t.v == m;
+    const int cand = (mine && t.idx >= 0) ? t.idx : INT32_MAX;
+    const int best = __reduce_min_sync(mask, cand);
+    A r;
+    r.v = m;
+    r.idx = best == INT32_MAX ? -1 : best;
+    return r;
+  }
   __device__ __forceinline__ static A combine(A a, A b) {
     if (a.idx < 0) return b;
     if (b.idx < 0) return a;

@@ -105,6 +105,8 @@ __device__ __forceinline__ A nxc_shfl_xor(const A &v, int mask) {
 // group beats it); the default is the sequential per-element step.
 template <class P, class = void> struct NxcHasMany { static constexpr bool v = false; };
 template <class P> struct NxcHasMany<P, typename std::enable_if<P::MANY>::type> { static constexpr bool v = true; };
+template <class P, class = void> struct NxcHasWarp { static constexpr bool v = false; };
+template <class P> struct NxcHasWarp<P, typename std::enable_if<P::WARP>::type> { static constexpr bool v = true; };
 template <class P, int N>
 __device__ __forceinline__ void nxc_step_many(typename P::A &acc, const typename P::S (&vals)[N], int64_t r0, int64_t rs) {
   if constexpr (NxcHasMany<P>::v) {
@@ -260,7 +262,14 @@ nxc_fold_short_kernel(const typename P::S *__restrict__ in, typename P::SO *__re
   for (int g = 0; g < G; g++) {
     A t = accg[g];
     if (TPR <= 32) {
-      for (int m = TPR >> 1; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
+      if constexpr (NxcHasWarp<P>::v) {
+        const unsigned gmask = TPR == 32 ? 0xffffffffu : (((1u << TPR) - 1u) << ((threadIdx.x & 31) & ~(TPR - 1)));
+        t = P::warp_combine(t, TPR, gmask);
+      } else {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1)
+          if (m < TPR) t = P::combine(t, nxc_shfl_xor(t, m));
+      }
     } else {
       for (int m = 16; m > 0; m >>= 1) t = P::combine(t, nxc_shfl_xor(t, m));
       __syncthreads();

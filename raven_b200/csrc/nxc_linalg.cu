@@ -233,6 +233,165 @@ nxc_qr_kernel(T *work, T *qbuf, T *taubuf, int64_t m, int64_t n, int64_t nq) {
   }
 }
 
+
+// ---- eigh: Hermitian eigendecomposition by parallel cyclic Jacobi ----------------------------------
+// The reference tridiagonalises and runs implicit-shift QL (nx_c_eigh.c); eigenvalues are unique
+// and eigenvectors unique up to a phase per column, so any convergent method meets its contract
+// (eigenvalues ascending and always f64, eigenvectors in the input dtype, LOWER triangle read,
+// "eigenvalue iteration did not converge" on failure). Jacobi is the GPU-shaped choice: a
+// round-robin schedule gives n/2 DISJOINT rotations per step, so a step is two fully parallel
+// passes over the matrix (columns, then rows) plus one over V, one CTA per batch matrix.
+// For the pivot block [[alpha, a], [conj a, beta]]: tau = (beta - alpha) / (2|a|),
+// t = sign(tau) / (|tau| + sqrt(1 + tau^2)), c = 1/sqrt(1 + t^2), s = t c, u = a/|a|,
+// J = [[c, s u], [-s conj u, c]], A <- J^H A J, V <- V J.
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_eigh_kernel(T *work, T *vbuf, double *wout, int64_t n, int vectors, int max_sweeps, int *status) {
+  typedef LA<T> L;
+  typedef typename L::R R;
+  extern __shared__ unsigned char eigh_smem[];
+  const int64_t np_ = n + (n & 1);            // even player count; player n (if any) sits out
+  const int64_t half = np_ / 2;
+  R *rc = (R *)eigh_smem;                      // per pair: c
+  R *rs = rc + half;                           // per pair: s
+  T *ru = (T *)(rs + half);                    // per pair: u (phase)
+  int *pp = (int *)(ru + half), *pq = pp + half;
+  __shared__ R red[NXC_LA_THREADS / 32];
+  T *A = work + (int64_t)blockIdx.x * n * n;
+  T *V = vbuf + (int64_t)blockIdx.x * n * n;
+  // Hermitian from the lower triangle; V = I
+  for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int64_t i = e / n, j = e - i * n;
+    if (j > i) A[e] = L::conj(A[j * n + i]);
+    else if (j == i) A[e] = L::mk(L::real(A[e]), (R)0);
+    V[e] = i == j ? L::mk((R)1, (R)0) : L::mk((R)0, (R)0);
+  }
+  __syncthreads();
+  bool converged = n <= 1;
+  for (int sweep = 0; sweep < max_sweeps && !converged; sweep++) {
+    R offp = (R)0, allp = (R)0;
+    for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const R v2 = L::norm2(A[e]);
+      allp += v2;
+      if (e / n != e % n) offp += v2;
+    }
+    const R off = nxc_la_block_sum<R>(offp, red);
+    const R all = nxc_la_block_sum<R>(allp, red);
+    const R eps = sizeof(R) == 4 ? (R)1e-7 : (R)1e-15;
+    if (!(off > eps * eps * all)) { converged = true; break; }
+    for (int64_t step = 0; step < np_ - 1; step++) {
+      // round-robin: player 0 fixed, the others rotate; pair i = (seat i, seat np-1-i)
+      for (int64_t i = threadIdx.x; i < half; i += blockDim.x) {
+        auto seat = [&](int64_t k) -> int64_t { return k == 0 ? 0 : 1 + (k - 1 + (np_ - 1) - step) % (np_ - 1); };
+        int64_t p = seat(i), q = seat(np_ - 1 - i);
+        if (p > q) { const int64_t t = p; p = q; q = t; }
+        R c = (R)1, sn = (R)0;
+        T u = L::mk((R)1, (R)0);
+        if (q < n) {
+          const T a = A[p * n + q];
+          const R ab = L::rsqrt_(L::norm2(a));
+          if (ab > (R)0) {
+            const R tau = (L::real(A[q * n + q]) - L::real(A[p * n + p])) / ((R)2 * ab);
+            const R t = (tau >= (R)0 ? (R)1 : (R)-1) / (fabs(tau) + L::rsqrt_((R)1 + tau * tau));
+            c = (R)1 / L::rsqrt_((R)1 + t * t);
+            sn = t * c;
+            u = L::divr(a, ab);
+          }
+        } else {
+          q = -1;
+        }
+        rc[i] = c; rs[i] = sn; ru[i] = u; pp[i] = (int)p; pq[i] = (int)q;
+      }
+      __syncthreads();
+      // columns: A <- A J and V <- V J   (x_p' = c x_p - s conj(u) x_q ; x_q' = s u x_p + c x_q)
+      for (int64_t e = threadIdx.x; e < half * n; e += blockDim.x) {
+        const int64_t i = e / n, r = e - i * n;
+        const int p = pp[i], q = pq[i];
+        if (q < 0 || rs[i] == (R)0) continue;
+        const T su = L::mk(rs[i] * L::real(ru[i]), rs[i] * L::imag(ru[i]));
+        const T suc = L::conj(su);
+        const R c = rc[i];
+        T xp = A[r * n + p], xq = A[r * n + q];
+        A[r * n + p] = L::sub(L::mk(c * L::real(xp), c * L::imag(xp)), L::mul(suc, xq));
+        A[r * n + q] = L::add(L::mul(su, xp), L::mk(c * L::real(xq), c * L::imag(xq)));
+        if (vectors) {
+          xp = V[r * n + p]; xq = V[r * n + q];
+          V[r * n + p] = L::sub(L::mk(c * L::real(xp), c * L::imag(xp)), L::mul(suc, xq));
+          V[r * n + q] = L::add(L::mul(su, xp), L::mk(c * L::real(xq), c * L::imag(xq)));
+        }
+      }
+      __syncthreads();
+      // rows: A <- J^H A   (y_p' = c y_p - s u y_q ; y_q' = s conj(u) y_p + c y_q)
+      for (int64_t e = threadIdx.x; e < half * n; e += blockDim.x) {
+        const int64_t i = e / n, r = e - i * n;
+        const int p = pp[i], q = pq[i];
+        if (q < 0 || rs[i] == (R)0) continue;
+        const T su = L::mk(rs[i] * L::real(ru[i]), rs[i] * L::imag(ru[i]));
+        const T suc = L::conj(su);
+        const R c = rc[i];
+        const T yp = A[p * n + r], yq = A[q * n + r];
+        A[p * n + r] = L::sub(L::mk(c * L::real(yp), c * L::imag(yp)), L::mul(su, yq));
+        A[q * n + r] = L::add(L::mul(suc, yp), L::mk(c * L::real(yq), c * L::imag(yq)));
+      }
+      __syncthreads();
+      // the pivots are zero by construction, the diagonal real
+      for (int64_t i = threadIdx.x; i < half; i += blockDim.x) {
+        const int p = pp[i], q = pq[i];
+        if (q < 0 || rs[i] == (R)0) continue;
+        A[p * n + q] = L::mk((R)0, (R)0);
+        A[q * n + p] = L::mk((R)0, (R)0);
+        A[p * n + p] = L::mk(L::real(A[p * n + p]), (R)0);
+        A[q * n + q] = L::mk(L::real(A[q * n + q]), (R)0);
+      }
+      __syncthreads();
+    }
+  }
+  if (!converged) {
+    // one more look: the last sweep may have finished the job
+    R offp = (R)0, allp = (R)0;
+    for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const R v2 = L::norm2(A[e]);
+      allp += v2;
+      if (e / n != e % n) offp += v2;
+    }
+    const R off = nxc_la_block_sum<R>(offp, red);
+    const R all = nxc_la_block_sum<R>(allp, red);
+    const R eps = sizeof(R) == 4 ? (R)1e-6 : (R)1e-14;
+    if (off > eps * eps * all) {
+      if (threadIdx.x == 0) atomicExch(status, 3);
+      return;
+    }
+  }
+  // ascending eigenvalues with their columns: rank by (value, position), then permute through
+  // the (now free) work matrix
+  double *w = wout + (int64_t)blockIdx.x * n;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const R dj = L::real(A[j * n + j]);
+    int64_t rank = 0;
+    for (int64_t k = 0; k < n; k++) {
+      const R dk = L::real(A[k * n + k]);
+      rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+    }
+    w[rank] = (double)dj;
+    pp[0] = 0;  // (shared scratch no longer needed; keeps the compiler from hoisting)
+    // park the rank in the strict upper triangle's first row is unsafe; recompute below instead
+  }
+  __syncthreads();
+  if (vectors) {
+    for (int64_t e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int64_t r = e / n, j = e - r * n;
+      const R dj = L::real(A[j * n + j]);
+      int64_t rank = 0;
+      for (int64_t k = 0; k < n; k++) {
+        const R dk = L::real(A[k * n + k]);
+        rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+      }
+      // the diagonal must survive until every thread has ranked: write to a second buffer
+      work[((int64_t)gridDim.x + blockIdx.x) * n * n + r * n + rank] = V[e];
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static int nxc_la_compute_dtype(int dt) {
   switch (dt) {
@@ -404,5 +563,86 @@ extern "C" nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor
   nxc_free(ctx, wbuf);
   if (qbuf) nxc_free(ctx, qbuf);
   if (tbuf) nxc_free(ctx, tbuf);
+  return nxc_la_fail(ctx, s);
+}
+
+static const char NXC_LA_NO_CONVERGE[] = "eigenvalue iteration did not converge";
+
+// eigh / eigvalsh (reference: caml_nx_c_eigh, nx_c_eigh.c; veneer backend_c/nx_backend.ml:627-648).
+// `w` is f64 [batch, n]; `v` (input dtype, input shape) is written only when vectors != 0.
+extern "C" nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tensor *v, const nxc_tensor *in, int vectors) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(w))) return nxc_la_fail(ctx, s);
+  if (in->ndim < 2 || w->ndim != in->ndim - 1) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t n = in->shape[in->ndim - 1];
+  if (in->shape[in->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_NOT_SQUARE);
+  if (w->dtype != NXC_F64 || w->shape[w->ndim - 1] != n) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int cdt = nxc_la_compute_dtype(in->dtype);
+  if (cdt < 0) return nxc_la_fail(ctx, NXC_LA_NOT_FLOAT);
+  int64_t nbatch = 1;
+  for (int i = 0; i < in->ndim - 2; i++) {
+    if (w->shape[i] != in->shape[i]) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= in->shape[i];
+  }
+  if (vectors) {
+    if ((s = nxc_check_tensor(v))) return nxc_la_fail(ctx, s);
+    if (v->ndim != in->ndim || v->dtype != in->dtype) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    for (int i = 0; i < in->ndim; i++)
+      if (v->shape[i] != in->shape[i]) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  }
+  if (n == 0 || nbatch == 0) return NXC_OK;
+  const size_t esz = (size_t)nxc_elem_size(cdt);
+  // work holds two n x n matrices per batch entry: A (first half) and the sorted eigenvectors
+  nxc_tensor aw, vw, ww;
+  void *abuf = NULL, *vbuf = NULL, *wbuf = NULL;
+  int *st = NULL;
+  if ((s = nxc_alloc(ctx, 2 * (size_t)nbatch * (size_t)(n * n) * esz, &abuf))) return nxc_la_fail(ctx, s);
+  aw = *in;
+  aw.dtype = cdt; aw.offset = 0; aw.data = abuf;
+  { int64_t stv = 1; for (int d = aw.ndim - 1; d >= 0; d--) { aw.strides[d] = stv; stv *= aw.shape[d]; } }
+  s = nxc_alloc(ctx, (size_t)nbatch * (size_t)(n * n) * esz, &vbuf);
+  if (!s) s = nxc_alloc(ctx, (size_t)nbatch * (size_t)n * sizeof(double), &wbuf);
+  if (!s) s = nxc_alloc(ctx, sizeof(int), (void **)&st);
+  if (!s) s = nxc_memset(ctx, st, 0, sizeof(int));
+  if (!s) s = nxc_la_move(ctx, &aw, in);
+  if (!s) {
+    const int64_t half = (n + (n & 1)) / 2;
+    NXC_LA_DISPATCH(cdt, {
+      const size_t smem = (size_t)half * (2 * sizeof(typename LA<T>::R) + sizeof(T) + 2 * sizeof(int)) + 16;
+      if (smem > 200 * 1024) s = NXC_ERR_TOO_LARGE;
+      else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(nxc_eigh_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nxc_eigh_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, smem, ctx->stream>>>((T *)abuf, (T *)vbuf, (double *)wbuf, n,
+                                                                                  vectors, 60, st);
+      }
+    })
+    ctx->launches++;
+    if (!s && cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "eigh");
+  }
+  if (!s) {
+    s = nxc_la_status(ctx, st);
+    if (s == NXC_LA_NOT_PD || s == NXC_LA_SINGULAR) s = NXC_OK;
+  }
+  if (!s) {
+    int h = 0;
+    NXC_CUDA_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h == 3) s = NXC_LA_NO_CONVERGE;
+  }
+  if (!s) {
+    ww = *w;
+    ww.offset = 0; ww.data = wbuf;
+    { int64_t stv = 1; for (int d = ww.ndim - 1; d >= 0; d--) { ww.strides[d] = stv; stv *= ww.shape[d]; } }
+    s = nxc_copy(ctx, w, &ww);
+  }
+  if (!s && vectors) {
+    vw = aw;
+    vw.data = (char *)abuf + (size_t)nbatch * (size_t)(n * n) * esz;  // sorted eigenvectors
+    s = nxc_la_move(ctx, v, &vw);
+  }
+  nxc_free(ctx, abuf);
+  if (vbuf) nxc_free(ctx, vbuf);
+  if (wbuf) nxc_free(ctx, wbuf);
+  if (st) nxc_free(ctx, st);
   return nxc_la_fail(ctx, s);
 }

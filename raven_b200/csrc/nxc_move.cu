@@ -257,8 +257,22 @@ static unsigned grid_for(nxc_ctx *ctx, int64_t total) {
     default: { typedef uint4 T; CALL; } break;                                    \
   }
 
+static nxc_status gather_impl(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data, const nxc_tensor *idx, int axis,
+                              bool checked);
 extern "C" nxc_status nxc_gather(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
                                  const nxc_tensor *idx, int axis) {
+  return gather_impl(ctx, out, data, idx, axis, true);
+}
+// The same gather for indices the backend produced itself (argmax / argmin / argsort results,
+// as the sharded argreduce reads the local extreme back at the winning index): out-of-range
+// indices are still never dereferenced, but the range flag is not read back, so the call does
+// not drain the stream.
+extern "C" nxc_status nxc_gather_trusted(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
+                                         const nxc_tensor *idx, int axis) {
+  return gather_impl(ctx, out, data, idx, axis, false);
+}
+static nxc_status gather_impl(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data, const nxc_tensor *idx, int axis,
+                              bool checked) {
   nxc_status s;
   if ((s = nxc_check_tensor(out)) || (s = nxc_check_tensor(data)) || (s = nxc_check_tensor(idx))) return fail(ctx, s);
   if (nxc_is_packed(out->dtype)) return fail(ctx, NXC_ERR_PACKED);
@@ -278,7 +292,7 @@ extern "C" nxc_status nxc_gather(nxc_ctx *ctx, const nxc_tensor *out, const nxc_
   const int32_t *ib = (const int32_t *)idx->data + idx->offset;
   BY_SIZE(es, (gather_kernel<T><<<grid_for(ctx, a.total), 256, 0, ctx->stream>>>((T *)ob, (const T *)db, ib, a, flag)))
   NXC_LAUNCH_CHECK(ctx);
-  return fail(ctx, oob_check(ctx, flag));
+  return checked ? fail(ctx, oob_check(ctx, flag)) : NXC_OK;
 }
 
 template <int DT, bool OK> struct ScatterAdd {

@@ -119,6 +119,15 @@ def sharded_reduce(x_local, op: str, axes, comm, backend=B):
     return comm.allreduce(backend.contiguous(part), op)
 
 
+def _gather_own(backend, data, idx):
+    """gather along axis 0 at indices the backend's own argreduce produced: no range read-back
+    (a checked gather drains the stream: measured +0.16 ms on a 0.17 ms sharded argmax)."""
+    try:
+        return backend.gather(data, idx, 0, trusted=True)
+    except TypeError:  # a backend double without the flag (tests)
+        return backend.gather(data, idx, 0)
+
+
 def sharded_argreduce(x_local, is_max: bool, axis: int, slab_offset: int, comm, backend=B):
     """argmax/argmin along `axis`; indices are global when axis == 0 is the sharded axis."""
     fn = backend.argmax if is_max else backend.argmin
@@ -130,13 +139,13 @@ def sharded_argreduce(x_local, is_max: bool, axis: int, slab_offset: int, comm, 
     idx = backend.reshape(idxk, tuple(idxk.shape[1:]))
     # the local extreme is read back at the winning index (one element per output) instead of
     # a second pass over the slab; it is NaN exactly when the local argreduce picked a NaN
-    val = backend.reshape(backend.gather(x_local, idxk, 0), tuple(idx.shape))
+    val = backend.reshape(_gather_own(backend, x_local, idxk), tuple(idx.shape))
     gidx = backend.add(idx, backend.expand(backend.full(idx.context, D.int32, [], int(slab_offset)), idx.shape)
                        ) if len(idx.shape) else backend.add(idx, backend.full(idx.context, D.int32, [], int(slab_offset)))
     gv = comm.allgather(val)    # [world, ...]
     gi = comm.allgather(gidx)   # [world, ...]
     win = fn(gv, 0, True)       # which rank wins, first-NaN / first-tie = lowest rank
-    out = backend.gather(gi, win, 0)
+    out = _gather_own(backend, gi, win)
     return backend.reshape(out, tuple(idx.shape))
 
 
