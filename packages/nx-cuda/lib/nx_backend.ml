@@ -306,10 +306,26 @@ let qr ~reduced x =
   lift_linalg ~op:"qr" (fun () -> caml_qr q r x reduced);
   (q, r)
 
+(* ---- linalg tier 2 (backend_c/nx_backend.ml:627-648): eigenvalues are always float64; the
+   values-only call passes the input in the eigenvector slot, which the engine then ignores ---- *)
+external caml_eigh : (float, Dtype.float64_elt) t -> ('a, 'b) t -> ('a, 'b) t -> bool -> unit = "nx_cuda_eigh"
+
+let eigh_values x =
+  let nd = Array.length x.shape in
+  create_tensor x.context Dtype.Float64 (Array.append (Array.sub x.shape 0 (nd - 2)) [| x.shape.(nd - 1) |])
+
+let eigvalsh x =
+  let w = eigh_values x in
+  lift_linalg ~op:"eigvalsh" (fun () -> caml_eigh w x x false);
+  w
+
+let eigh x =
+  let w = eigh_values x and v = create_tensor x.context x.dtype x.shape in
+  lift_linalg ~op:"eigh" (fun () -> caml_eigh w v x true);
+  (w, v)
+
 (* ---- not yet behind the C ABI (scope table 8f rank 4): fail loudly, never fall back ---- *)
 let todo op = failwith (op ^ ": not implemented by nx-cuda")
 let svd ~full_matrices:_ _ = todo "svd"
 let eigvals _ = todo "eigvals"
 let eig _ = todo "eig"
-let eigvalsh _ = todo "eigvalsh"
-let eigh _ = todo "eigh"

@@ -331,3 +331,10 @@ CAMLprim value nx_cuda_qr(value vq, value vr, value vin, value vreduced) {
   if (s) raise_status("qr", CTX_OF(vq), s);
   CAMLreturn(Val_unit);
 }
+CAMLprim value nx_cuda_eigh(value vw, value vv, value vin, value vvectors) {
+  CAMLparam4(vw, vv, vin, vvectors);
+  nxc_tensor w, v, a; tensor_of_value(vw, &w); tensor_of_value(vv, &v); tensor_of_value(vin, &a);
+  nxc_status s = nxc_eigh(CTX_OF(vw), &w, &v, &a, Bool_val(vvectors));
+  if (s) raise_status(Bool_val(vvectors) ? "eigh" : "eigvalsh", CTX_OF(vw), s);
+  CAMLreturn(Val_unit);
+}
