@@ -196,6 +196,22 @@ NXC_API nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r
    otherwise, as the reference veneer does). Failure "eigenvalue iteration did not converge". */
 NXC_API nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w_f64, const nxc_tensor *v, const nxc_tensor *in,
                             int vectors);
+/* svd (linalg tier 3): replaces caml_nx_c_svd (reference: nx_c_svd.c:2943-2958, driver
+   nx_c_svd_run :2743-2938; veneer backend_c/nx_backend.ml:650-677). in [batch..., m, n], k = min(m, n):
+   `s_f64` [batch..., k] (always float64) receives the singular values, descending and non-negative;
+   `u` [batch..., m, k|m] and `vt` [batch..., k|n, n] (input dtype) receive U and V^H -- thin or full is
+   read off each output's shape, as the reference does. Failure "eigenvalue iteration did not
+   converge" (the reference's LA_ERR_NO_CONVERGE, lifted to Linalg_error by the veneer). */
+NXC_API nxc_status nxc_svd(nxc_ctx *ctx, const nxc_tensor *u, const nxc_tensor *s_f64, const nxc_tensor *vt,
+                           const nxc_tensor *in);
+/* eig / eigvals (linalg tier 3): replaces caml_nx_c_eig (reference: nx_c_eig.c:1310-1326, driver
+   nx_c_eig_run :1195-1298; veneer backend_c/nx_backend.ml:679-707). General square matrices of any
+   float / complex dtype; `w_c64` [batch..., n] and `v_c64` [batch..., n, n] are ALWAYS complex128;
+   eigenvector columns have unit 2-norm, no phase or order convention; `v_c64` is written only when
+   vectors != 0 (pass `w_c64` there otherwise, as the reference veneer does). Invalid_argument
+   "eig requires a float or complex dtype"; Failure "eigenvalue iteration did not converge". */
+NXC_API nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w_c64, const nxc_tensor *v_c64, const nxc_tensor *in,
+                           int vectors);
 
 /* ---- matmul ---------------------------------------------------------------
    replaces caml_nx_c_matmul (reference: nx_c_matmul.c:874-1108, 1271-1277).

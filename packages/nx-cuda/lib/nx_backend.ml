@@ -324,8 +324,35 @@ let eigh x =
   lift_linalg ~op:"eigh" (fun () -> caml_eigh w v x true);
   (w, v)
 
-(* ---- not yet behind the C ABI (scope table 8f rank 4): fail loudly, never fall back ---- *)
-let todo op = failwith (op ^ ": not implemented by nx-cuda")
-let svd ~full_matrices:_ _ = todo "svd"
-let eigvals _ = todo "eigvals"
-let eig _ = todo "eig"
+(* ---- linalg tier 3 (backend_c/nx_backend.ml:650-707): S is always float64 and the thin / full
+   choice travels in the U / V^H shapes; eig's outputs are always complex128 and the values-only
+   call passes [w] in the eigenvector slot, which the engine then ignores ---- *)
+external caml_svd : ('a, 'b) t -> (float, Dtype.float64_elt) t -> ('a, 'b) t -> ('a, 'b) t -> unit = "nx_cuda_svd"
+
+let svd ~full_matrices x =
+  let nd = Array.length x.shape in
+  let m = x.shape.(nd - 2) and n = x.shape.(nd - 1) in
+  let k = Int.min m n in
+  let batch = Array.sub x.shape 0 (nd - 2) in
+  let u = create_tensor x.context x.dtype (Array.append batch (if full_matrices then [| m; m |] else [| m; k |])) in
+  let s = create_tensor x.context Dtype.Float64 (Array.append batch [| k |]) in
+  let vt = create_tensor x.context x.dtype (Array.append batch (if full_matrices then [| n; n |] else [| k; n |])) in
+  lift_linalg ~op:"svd" (fun () -> caml_svd u s vt x);
+  (u, s, vt)
+
+external caml_eig :
+  (Complex.t, Dtype.complex64_elt) t -> (Complex.t, Dtype.complex64_elt) t -> ('a, 'b) t -> bool -> unit = "nx_cuda_eig"
+
+let eig_values x =
+  let nd = Array.length x.shape in
+  create_tensor x.context Dtype.Complex128 (Array.append (Array.sub x.shape 0 (nd - 2)) [| x.shape.(nd - 1) |])
+
+let eigvals x =
+  let w = eig_values x in
+  lift_linalg ~op:"eigvals" (fun () -> caml_eig w w x false);
+  w
+
+let eig x =
+  let w = eig_values x and v = create_tensor x.context Dtype.Complex128 x.shape in
+  lift_linalg ~op:"eig" (fun () -> caml_eig w v x true);
+  (w, v)

@@ -338,3 +338,18 @@ CAMLprim value nx_cuda_eigh(value vw, value vv, value vin, value vvectors) {
   if (s) raise_status(Bool_val(vvectors) ? "eigh" : "eigvalsh", CTX_OF(vw), s);
   CAMLreturn(Val_unit);
 }
+CAMLprim value nx_cuda_svd(value vu, value vs, value vvt, value vin) {
+  CAMLparam4(vu, vs, vvt, vin);
+  nxc_tensor u, sv, vt, a; tensor_of_value(vu, &u); tensor_of_value(vs, &sv); tensor_of_value(vvt, &vt); tensor_of_value(vin, &a);
+  nxc_status s = nxc_svd(CTX_OF(vu), &u, &sv, &vt, &a);
+  if (s) raise_status("svd", CTX_OF(vu), s);
+  CAMLreturn(Val_unit);
+}
+/* both eig and eigvals raise as "eig", like the reference stub (nx_c_eig.c:1310-1326) */
+CAMLprim value nx_cuda_eig(value vw, value vv, value vin, value vvectors) {
+  CAMLparam4(vw, vv, vin, vvectors);
+  nxc_tensor w, v, a; tensor_of_value(vw, &w); tensor_of_value(vv, &v); tensor_of_value(vin, &a);
+  nxc_status s = nxc_eig(CTX_OF(vw), &w, &v, &a, Bool_val(vvectors));
+  if (s) raise_status("eig", CTX_OF(vw), s);
+  CAMLreturn(Val_unit);
+}

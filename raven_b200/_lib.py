@@ -74,6 +74,8 @@ SYMBOLS = {
     "nxc_triangular_solve": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_qr": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_eigh": (_S, [_P, _T, _T, _T, ctypes.c_int]),
+    "nxc_svd": (_S, [_P, _T, _T, _T, _T]),
+    "nxc_eig": (_S, [_P, _T, _T, _T, ctypes.c_int]),
     "nxc_fft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
     "nxc_rfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "nxc_irfft": (_S, [_P, _T, _T, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int64]),

@@ -697,3 +697,43 @@ def eigh(x: Tensor):
     _reraise_linalg("eigh", lambda: _call(x.context, "eigh", x.context._lib.nxc_eigh, ctypes.byref(dw),
                                           ctypes.byref(dv), ctypes.byref(dx), 1))
     return w, v
+
+
+# ---- linalg tier 3: svd, eig / eigvals (backend_c/nx_backend.ml:650-707) ----------------------
+def svd(x: Tensor, full_matrices: bool = False):
+    """(U, S, V^H); S is float64 [batch..., k]; thin gives U m x k and V^H k x n, full gives m x m and
+    n x n -- the flag travels in the output shapes (backend_c/nx_backend.ml:653-677)."""
+    sh = list(x.shape)
+    m, n = sh[-2], sh[-1]
+    k = m if m < n else n
+    batch = sh[:-2]
+    u = _create(x.context, x.dtype, batch + ([m, m] if full_matrices else [m, k]))
+    s = _create(x.context, _dt.float64, batch + [k])
+    vt = _create(x.context, x.dtype, batch + ([n, n] if full_matrices else [k, n]))
+    du, ds, dv, dx = u._desc(), s._desc(), vt._desc(), x._desc()
+    _reraise_linalg("svd", lambda: _call(x.context, "svd", x.context._lib.nxc_svd, ctypes.byref(du), ctypes.byref(ds),
+                                         ctypes.byref(dv), ctypes.byref(dx)))
+    return u, s, vt
+
+
+def _eig_values(x: Tensor) -> Tensor:
+    return _create(x.context, _dt.complex128, tuple(x.shape[:-2]) + (x.shape[-1],))
+
+
+def eigvals(x: Tensor) -> Tensor:
+    """Eigenvalues only, always complex128; the stub raises as "eig" for both entry points
+    (nx_c_eig.c:1310-1326) and the values-only call passes `w` in the eigenvector slot."""
+    w = _eig_values(x)
+    dw, dx = w._desc(), x._desc()
+    _reraise_linalg("eigvals", lambda: _call(x.context, "eig", x.context._lib.nxc_eig, ctypes.byref(dw),
+                                             ctypes.byref(dw), ctypes.byref(dx), 0))
+    return w
+
+
+def eig(x: Tensor):
+    w = _eig_values(x)
+    v = _create(x.context, _dt.complex128, x.shape)
+    dw, dv, dx = w._desc(), v._desc(), x._desc()
+    _reraise_linalg("eig", lambda: _call(x.context, "eig", x.context._lib.nxc_eig, ctypes.byref(dw), ctypes.byref(dv),
+                                         ctypes.byref(dx), 1))
+    return w, v

@@ -646,3 +646,213 @@ extern "C" nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tens
   if (st) nxc_free(ctx, st);
   return nxc_la_fail(ctx, s);
 }
+
+// ---- linalg tier 3: svd, eig / eigvals ----------------------------------------------------------
+// Kernel bodies: nxc_linalg3.cuh (shared with the CPU emulation the test suite runs).
+#include "nxc_linalg3.cuh"
+
+template <class T> struct La3Map;
+template <> struct La3Map<float> { typedef float E; };
+template <> struct La3Map<double> { typedef double E; };
+template <> struct La3Map<cf32> { typedef La3C32 E; };
+template <> struct La3Map<cf64> { typedef La3C64 E; };
+
+__device__ __forceinline__ La3Thr nxc_la3_thr() {
+  La3Thr t;
+  t.tid = (int)threadIdx.x; t.nt = (int)blockDim.x;
+  t.lane = (int)(threadIdx.x & 31); t.lanes = 32;
+  t.warp = (int)(threadIdx.x >> 5); t.nwarps = (int)(blockDim.x >> 5);
+  return t;
+}
+
+struct NxcSvdArgs {
+  void *gt, *wt, *ut, *uo, *vho;
+  double *sig, *sg, *rown;
+  int *rk;
+  Cd *coef;
+  int64_t m, n, ucols, vrows;
+  int *status;
+};
+
+template <class E>
+__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_svd_kernel(const __grid_constant__ NxcSvdArgs a) {
+  __shared__ double red[NXC_LA_THREADS];
+  __shared__ int flags[2];
+  const int64_t b = blockIdx.x;
+  const bool tall = a.m >= a.n;
+  const int64_t pr = tall ? a.m : a.n, pc = tall ? a.n : a.m, ncu = tall ? a.ucols : a.vrows;
+  la3_svd_body<E>(nxc_la3_thr(), (E *)a.gt + b * pc * pr, (E *)a.wt + b * pc * pc, (E *)a.ut + b * ncu * pr,
+                  (E *)a.uo + b * a.m * a.ucols, (E *)a.vho + b * a.vrows * a.n, a.sig + b * pc, a.sg + b * pc, a.rk + b * pc,
+                  a.rown + b * pr, a.coef + b * pr, red, flags, a.m, a.n, a.ucols, a.vrows, 60, a.status);
+}
+
+struct NxcEigArgs {
+  Cd *h, *z, *x, *vo, *w, *vs, *rs;
+  double *rc;
+  int64_t n;
+  int vectors;
+  int *status;
+};
+
+__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eig_kernel(const __grid_constant__ NxcEigArgs a) {
+  __shared__ double red[NXC_LA_THREADS];
+  const int64_t b = blockIdx.x, n = a.n, nn = a.n * a.n;
+  la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, a.vs + b * n, a.rc + b * n,
+               a.rs + b * n, red, n, a.vectors, a.status);
+}
+
+// contiguous descriptor [batch..., rows, cols] of dtype dt over `data`, batch dims taken from `like`
+static void nxc_la_desc(const nxc_tensor *like, int dt, int64_t rows, int64_t cols, void *data, nxc_tensor *w) {
+  *w = *like;
+  w->dtype = dt; w->offset = 0; w->data = data;
+  w->shape[w->ndim - 2] = rows;
+  w->shape[w->ndim - 1] = cols;
+  int64_t st = 1;
+  for (int d = w->ndim - 1; d >= 0; d--) { w->strides[d] = st; st *= w->shape[d]; }
+}
+
+static nxc_status nxc_la_status3(nxc_ctx *ctx, int *dev_status) {
+  int h = 0;
+  NXC_CUDA_TRY(ctx, cudaMemcpyAsync(&h, dev_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NXC_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return h == 3 ? NXC_LA_NO_CONVERGE : NXC_OK;
+}
+
+// svd (reference: caml_nx_c_svd, nx_c_svd.c:2943-2958; driver nx_c_svd_run :2743-2938; veneer
+// backend_c/nx_backend.ml:650-677). s is f64 [batch, k]; u [batch, m, k|m]; vt [batch, k|n, n]: thin or
+// full is read off each output's shape, as the reference does.
+extern "C" nxc_status nxc_svd(nxc_ctx *ctx, const nxc_tensor *u, const nxc_tensor *sv, const nxc_tensor *vt,
+                              const nxc_tensor *in) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(u)) || (s = nxc_check_tensor(sv)) || (s = nxc_check_tensor(vt)))
+    return nxc_la_fail(ctx, s);
+  if (in->ndim < 2 || u->ndim != in->ndim || vt->ndim != in->ndim || sv->ndim != in->ndim - 1)
+    return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t m = in->shape[in->ndim - 2], n = in->shape[in->ndim - 1], k = m < n ? m : n;
+  const int64_t ucols = u->shape[u->ndim - 1], vrows = vt->shape[vt->ndim - 2];
+  if (u->shape[u->ndim - 2] != m || vt->shape[vt->ndim - 1] != n || sv->shape[sv->ndim - 1] != k ||
+      (ucols != k && ucols != m) || (vrows != k && vrows != n))
+    return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int cdt = nxc_la_compute_dtype(in->dtype);
+  if (cdt < 0) return nxc_la_fail(ctx, NXC_LA_NOT_FLOAT);
+  if (u->dtype != in->dtype || vt->dtype != in->dtype || sv->dtype != NXC_F64) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  int64_t nbatch = 1;
+  for (int i = 0; i < in->ndim - 2; i++) {
+    if (u->shape[i] != in->shape[i] || vt->shape[i] != in->shape[i] || sv->shape[i] != in->shape[i])
+      return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= in->shape[i];
+  }
+  if (k == 0 || nbatch == 0) return NXC_OK;
+  const bool tall = m >= n;
+  const int64_t pr = tall ? m : n, pc = k, ncu = tall ? ucols : vrows;
+  const size_t esz = (size_t)nxc_elem_size(cdt), nb = (size_t)nbatch;
+  // one allocation, carved: gt, wt, ut, uo, vho (compute type), coef (Cd), sig, sg, rown (f64), rk (int), status
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_gt = carve(nb * pc * pr * esz), o_wt = carve(nb * pc * pc * esz), o_ut = carve(nb * ncu * pr * esz);
+  const size_t o_uo = carve(nb * m * ucols * esz), o_vho = carve(nb * vrows * n * esz), o_coef = carve(nb * pr * sizeof(Cd));
+  const size_t o_sig = carve(nb * pc * 8), o_sg = carve(nb * pc * 8), o_rown = carve(nb * pr * 8), o_rk = carve(nb * pc * 4);
+  const size_t o_st = carve(sizeof(int));
+  char *base = NULL;
+  if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
+  s = nxc_memset(ctx, base + o_st, 0, sizeof(int));
+  // gt = P^T without conjugation: the transposed view of A when tall, A itself when wide
+  nxc_tensor gd, src = *in;
+  nxc_la_desc(in, cdt, pc, pr, base + o_gt, &gd);
+  if (tall) {
+    const int r = in->ndim - 2, c = in->ndim - 1;
+    src.shape[r] = in->shape[c]; src.shape[c] = in->shape[r];
+    src.strides[r] = in->strides[c]; src.strides[c] = in->strides[r];
+  }
+  if (!s) s = nxc_la_move(ctx, &gd, &src);
+  if (!s) {
+    NxcSvdArgs a;
+    a.gt = base + o_gt; a.wt = base + o_wt; a.ut = base + o_ut; a.uo = base + o_uo; a.vho = base + o_vho;
+    a.sig = (double *)(base + o_sig); a.sg = (double *)(base + o_sg); a.rown = (double *)(base + o_rown);
+    a.rk = (int *)(base + o_rk); a.coef = (Cd *)(base + o_coef);
+    a.m = m; a.n = n; a.ucols = ucols; a.vrows = vrows; a.status = (int *)(base + o_st);
+    NXC_LA_DISPATCH(cdt, { nxc_svd_kernel<typename La3Map<T>::E><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a); })
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "svd");
+  }
+  if (!s) s = nxc_la_status3(ctx, (int *)(base + o_st));
+  if (!s) {
+    nxc_tensor d;
+    nxc_la_desc(in, cdt, m, ucols, base + o_uo, &d);
+    s = nxc_la_move(ctx, u, &d);
+    if (!s) { nxc_la_desc(in, cdt, vrows, n, base + o_vho, &d); s = nxc_la_move(ctx, vt, &d); }
+    if (!s) {
+      nxc_tensor sd = *sv;
+      sd.offset = 0; sd.data = base + o_sig;
+      int64_t stv = 1;
+      for (int dd = sd.ndim - 1; dd >= 0; dd--) { sd.strides[dd] = stv; stv *= sd.shape[dd]; }
+      s = nxc_copy(ctx, sv, &sd);
+    }
+  }
+  nxc_free(ctx, base);
+  return nxc_la_fail(ctx, s);
+}
+
+static const char NXC_EIG_NOT_FLOAT[] = "eig requires a float or complex dtype";
+#define NXC_EIG_MAX_N 46340  /* the reference's own bound (nx_c_eig.c:91-96) */
+static const char NXC_EIG_TOO_LARGE[] = "matrix dimension exceeds eig limit";
+
+// eig / eigvals (reference: caml_nx_c_eig, nx_c_eig.c:1310-1326; driver nx_c_eig_run :1195-1298; veneer
+// backend_c/nx_backend.ml:679-707). w is c64 [batch, n]; v c64 [batch, n, n], written only when vectors != 0.
+extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tensor *v, const nxc_tensor *in, int vectors) {
+  nxc_status s;
+  if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(w))) return nxc_la_fail(ctx, s);
+  if (vectors && (s = nxc_check_tensor(v))) return nxc_la_fail(ctx, s);
+  if (in->ndim < 2) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  const int64_t n = in->shape[in->ndim - 1];
+  if (in->shape[in->ndim - 2] != n) return nxc_la_fail(ctx, NXC_LA_NOT_SQUARE);
+  if (n > NXC_EIG_MAX_N) return nxc_la_fail(ctx, NXC_EIG_TOO_LARGE);
+  if (w->ndim != in->ndim - 1 || w->shape[w->ndim - 1] != n) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  if (vectors && (v->ndim != in->ndim || v->shape[v->ndim - 1] != n || v->shape[v->ndim - 2] != n))
+    return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  if (nxc_la_compute_dtype(in->dtype) < 0) return nxc_la_fail(ctx, NXC_EIG_NOT_FLOAT);
+  if (w->dtype != NXC_C64 || (vectors && v->dtype != NXC_C64)) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+  int64_t nbatch = 1;
+  for (int i = 0; i < in->ndim - 2; i++) {
+    if (w->shape[i] != in->shape[i] || (vectors && v->shape[i] != in->shape[i])) return nxc_la_fail(ctx, NXC_LA_SHAPE);
+    nbatch *= in->shape[i];
+  }
+  if (n == 0 || nbatch == 0) return NXC_OK;
+  const size_t nb = (size_t)nbatch, nn = (size_t)(n * n);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_h = carve(nb * nn * 16), o_z = carve(nb * nn * 16);
+  const size_t o_x = carve(vectors ? nb * nn * 16 : 16), o_vo = carve(vectors ? nb * nn * 16 : 16);
+  const size_t o_w = carve(nb * n * 16), o_vs = carve(nb * n * 16), o_rs = carve(nb * n * 16), o_rc = carve(nb * n * 8);
+  const size_t o_st = carve(sizeof(int));
+  char *base = NULL;
+  if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
+  s = nxc_memset(ctx, base + o_st, 0, sizeof(int));
+  nxc_tensor hd;
+  nxc_la_desc(in, NXC_C64, n, n, base + o_h, &hd);
+  if (!s) s = nxc_la_move(ctx, &hd, in);  // any float / complex storage -> complex double
+  if (!s) {
+    NxcEigArgs a;
+    a.h = (Cd *)(base + o_h); a.z = (Cd *)(base + o_z); a.x = (Cd *)(base + o_x); a.vo = (Cd *)(base + o_vo);
+    a.w = (Cd *)(base + o_w); a.vs = (Cd *)(base + o_vs); a.rs = (Cd *)(base + o_rs); a.rc = (double *)(base + o_rc);
+    a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st);
+    nxc_eig_kernel<<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "eig");
+  }
+  if (!s) s = nxc_la_status3(ctx, (int *)(base + o_st));
+  if (!s) {
+    nxc_tensor wd = *w;
+    wd.offset = 0; wd.data = base + o_w;
+    int64_t stv = 1;
+    for (int dd = wd.ndim - 1; dd >= 0; dd--) { wd.strides[dd] = stv; stv *= wd.shape[dd]; }
+    s = nxc_copy(ctx, w, &wd);
+  }
+  if (!s && vectors) {
+    nxc_tensor vd;
+    nxc_la_desc(in, NXC_C64, n, n, base + o_vo, &vd);
+    s = nxc_copy(ctx, v, &vd);
+  }
+  nxc_free(ctx, base);
+  return nxc_la_fail(ctx, s);
+}

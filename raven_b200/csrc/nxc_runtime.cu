@@ -161,6 +161,7 @@ extern "C" int nxc_status_is_invalid_argument(nxc_status s) {
                               "threefry: last axis must have extent 2",
                               // linalg preconditions (reference: la_raise, nx_c_linalg.h:310-318)
                               "linalg requires a float or complex dtype", "matrix must be square",
+                              "eig requires a float or complex dtype",
                               "operand shapes are incompatible"};
   for (size_t i = 0; i < sizeof inv / sizeof inv[0]; i++)
     if (strcmp(s, inv[i]) == 0) return 1;

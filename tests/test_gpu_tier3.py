@@ -1,0 +1,104 @@
+"""GPU parity of svd and eig / eigvals (linalg tier 3) through the C ABI:
+singular values and eigenvalue sets against the oracle (the reference binary on the GPU box), the
+vectors by their defining properties (unique only up to a phase), thin / full, tall / wide, batched,
+strided, rank-deficient and low-precision inputs, error classes."""
+import numpy as np
+import pytest
+
+import raven_b200.backend as B
+from raven_b200 import InvalidArgument
+from tests import harness as H
+from tests.golden.make_golden_tier3 import eig_inputs, svd_inputs
+from tests.test_oracle_tier3 import TOL, check_eig, check_svd, eig_set_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _widen(dt, bits):
+    return (bits.view(np.float16) if dt == "f16" else H.bf16_bits_to_f32(bits)).astype(np.float64)
+
+
+def test_svd_matches_oracle(ctx, oracle):
+    for key, hv in svd_inputs():
+        dt = key.split("|")[1]
+        want = oracle.svd(hv, False)[1].numpy()
+        for full in (False, True):
+            u, s, vh = B.svd(H.upload(ctx, hv), full_matrices=full)
+            u, s, vh = H.download(u), H.download(s), H.download(vh)
+            assert np.abs(s - want).max() <= 20 * TOL[dt] * max(1.0, want.max()), key
+            check_svd(u, s, vh, hv, dt, key, full, tol_scale=2.0)
+
+
+def test_svd_strided_views_and_half_precision(ctx, oracle):
+    rng = np.random.default_rng(75)
+    a = rng.standard_normal((2, 9, 6))
+    hv = H.HostView.from_array(a, "f64").permute([0, 2, 1]).flip([False, True, False])
+    want = oracle.svd(hv, False)[1].numpy()
+    u, s, vh = B.svd(H.upload(ctx, hv))
+    assert np.abs(H.download(s) - want).max() <= 1e-12 * want.max()
+    check_svd(H.download(u), H.download(s), H.download(vh), hv, "f64", "strided", False)
+    # f16 / bf16 compute in f32 and round once on the way out (nx_c_linalg.h:183-200)
+    for dt, tol in (("f16", 2e-3), ("bf16", 1.6e-2)):
+        hv = H.HostView(H.to_storage(dt, rng.standard_normal((5, 4))).reshape(-1), dt, [5, 4])
+        want = oracle.svd(hv, False)[1].numpy()
+        u, s, vh = B.svd(H.upload(ctx, hv))
+        s = H.download(s)
+        assert np.abs(s - want).max() <= 1e-5 * want.max(), dt
+        U, Vh = _widen(dt, H.download(u)), _widen(dt, H.download(vh))
+        assert np.abs((U * s) @ Vh - _widen(dt, hv.numpy())).max() <= 8 * tol * want.max(), dt
+
+
+def test_svd_larger(ctx):
+    rng = np.random.default_rng(76)
+    for shp, dt in (((2, 150, 70), "c64"), ((70, 200), "f32")):
+        a = rng.standard_normal(shp)
+        if dt[0] == "c":
+            a = a + 1j * rng.standard_normal(shp)
+        hv = H.HostView.from_array(a, dt)
+        for full in (False, True):
+            u, s, vh = B.svd(H.upload(ctx, hv), full_matrices=full)
+            u, s, vh = H.download(u), H.download(s), H.download(vh)
+            want = np.linalg.svd(hv.numpy().astype(np.complex128), compute_uv=False)
+            assert np.abs(s - want).max() <= 20 * TOL[dt] * want.max()
+            check_svd(u, s, vh, hv, dt, str(shp), full, tol_scale=2.0)
+
+
+def test_eig_matches_oracle(ctx, oracle):
+    for key, hv in eig_inputs():
+        want = oracle.eig(hv, False).numpy()
+        w, v = B.eig(H.upload(ctx, hv))
+        w, v = H.download(w), H.download(v)
+        assert eig_set_err(w, want) <= 1e-9 * max(1.0, np.abs(want).max()), key
+        check_eig(w, v, hv, key)
+        wv = H.download(B.eigvals(H.upload(ctx, hv)))
+        assert np.array_equal(wv, w), key
+
+
+def test_eig_larger_strided_and_defective(ctx):
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((3, 80, 80))
+    hv = H.HostView.from_array(a, "f64").permute([0, 2, 1])
+    w, v = B.eig(H.upload(ctx, hv))
+    w, v = H.download(w), H.download(v)
+    want = np.linalg.eigvals(np.swapaxes(a, -1, -2))
+    assert eig_set_err(w, want) <= 1e-9 * np.abs(want).max()
+    check_eig(w, v, hv, "80x80")
+    t = np.triu(np.ones((40, 40)))
+    w, v = B.eig(H.upload(ctx, H.HostView.from_array(t, "f32")))
+    w, v = H.download(w), H.download(v)
+    assert np.abs(w - 1).max() <= 1e-12 and np.isfinite(v).all()
+    assert np.abs(t @ v - v * w[None, :]).max() <= 1e-10
+
+
+def test_tier3_errors_and_empty(ctx):
+    up = lambda a, dt: H.upload(ctx, H.HostView.from_array(a, dt))
+    with pytest.raises(InvalidArgument, match="eig: matrix must be square"):
+        B.eig(up(np.ones((2, 3)), "f64"))
+    with pytest.raises(InvalidArgument, match="eig: matrix must be square"):
+        B.eigvals(up(np.ones((2, 3)), "f64"))
+    with pytest.raises(InvalidArgument, match="eig: eig requires a float or complex dtype"):
+        B.eigvals(up(np.ones((2, 2), dtype=np.int32), "i32"))
+    with pytest.raises(InvalidArgument, match="svd: linalg requires a float or complex dtype"):
+        B.svd(up(np.ones((2, 2), dtype=np.int32), "i32"))
+    u, s, vh = B.svd(up(np.zeros((0, 3)), "f64"), full_matrices=True)
+    assert tuple(u.shape) == (0, 0) and tuple(s.shape) == (0,) and tuple(vh.shape) == (3, 3)
