@@ -106,7 +106,12 @@ NXC_API uint64_t nxc_launch_count(nxc_ctx *ctx);
    nx_c_matmul.c:1229-1237). */
 NXC_API int nxc_status_is_invalid_argument(nxc_status s);
 NXC_API int64_t nxc_elem_size(int dtype); /* 0 for packed int4/uint4 (reference: nx_c.h:309-321) */
-NXC_API int nxc_set_matmul_mode(nxc_ctx *ctx, const char *mode); /* "f32" | "tf32"; 0 ok */
+/* How f32 operands are multiplied; 0 ok, -1 unknown mode. "f32" (default): f32-class accuracy --
+   products of a few GFLOP and more run on the tensor cores as 3xTF32 (hi / lo split, error inside
+   the classical K*u sgemm bound), smaller ones on the CUDA-core kernel; "ieee": always the
+   CUDA-core kernel (every product and sum rounded to nearest); "tf32": plain tf32 operands,
+   1e-3 relative, opt-in. bf16 / f16 always use the tensor cores with f32 accumulation. */
+NXC_API int nxc_set_matmul_mode(nxc_ctx *ctx, const char *mode);
 
 NXC_API nxc_status nxc_alloc(nxc_ctx *ctx, size_t bytes, void **dptr); /* stream-ordered, cached */
 NXC_API nxc_status nxc_free(nxc_ctx *ctx, void *dptr);                 /* ordered after in-flight work */

@@ -135,9 +135,10 @@ class Tensor:
     """The handle `('a,'b) t` = {buffer; shape; strides; offset; dtype; context}
     (reference: backend_c/nx_backend.ml:36-43)."""
 
-    __slots__ = ("buffer", "shape", "strides", "offset", "dtype", "context")
+    __slots__ = ("buffer", "shape", "strides", "offset", "dtype", "context", "_d")
 
     def __init__(self, buffer, shape, strides, offset, dtype, context):
+        self._d = None
         self.buffer = buffer
         self.shape = tuple(int(s) for s in shape)
         self.strides = tuple(int(s) for s in strides)
@@ -146,6 +147,9 @@ class Tensor:
         self.context = context
 
     def _desc(self) -> NxcTensor:
+        # a handle is immutable and the engine only reads descriptors: build once, reuse per op
+        if self._d is not None:
+            return self._d
         if len(self.shape) > 32:
             raise Failure("ndim exceeds NX_C_MAX_NDIM")
         t = NxcTensor()
@@ -156,6 +160,7 @@ class Tensor:
             t.shape[i] = s
             t.strides[i] = st
         t.offset = self.offset
+        self._d = t
         return t
 
     def __repr__(self):

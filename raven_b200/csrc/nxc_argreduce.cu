@@ -128,6 +128,9 @@ template <int IS_MAX, int DT> struct ArgP {
   }
   __device__ __forceinline__ static SO finish(A a) { return a.idx < 0 ? 0 : a.idx; }
 };
+template <int IS_MAX, int DT> struct NxcFoldPipe<ArgP<IS_MAX, DT>> {
+  static constexpr bool v = sizeof(typename ArgP<IS_MAX, DT>::S) >= 8;
+};
 
 extern "C" nxc_status nxc_argreduce(nxc_ctx *ctx, int is_max, const nxc_tensor *out,
                                     const nxc_tensor *in, int axis) {

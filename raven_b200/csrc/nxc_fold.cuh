@@ -119,6 +119,10 @@ __device__ __forceinline__ void nxc_step_many(typename P::A &acc, const typename
 
 // rows in flight per thread group on the short-row path: small accumulators afford 8
 template <class P> struct NxcFoldG { static constexpr int v = sizeof(typename P::A) <= 8 ? 8 : 4; };
+// short-row path: software-pipeline the row loop (next iteration's loads before this one's fold)?
+// Needed for the 8-byte types (see the kernel); it doubles the registers holding loaded values, so
+// policies whose fold step is itself heavy (argreduce on 4-byte types) opt out and keep 4 CTAs/SM.
+template <class P> struct NxcFoldPipe { static constexpr bool v = true; };
 
 // offsets of output `o`: one kept dim (the usual [rows, R] case) is a multiplication, not a
 // decode -- cheap enough to redo at the store instead of keeping per-row offsets in registers
@@ -245,18 +249,55 @@ nxc_fold_short_kernel(const typename P::S *__restrict__ in, typename P::SO *__re
   const int64_t gstep = (int64_t)RPB * kin;
   const S *p = in + o_base * kin + (VEC > 1 ? (int64_t)tr * VEC : (int64_t)tr * a.s_inner);
   const int64_t pstep = VEC > 1 ? (int64_t)step : (int64_t)step * a.s_inner;
-  for (int r = tr * VEC; r < R; r += step, p += pstep) {
-    S v[G][VEC];
+  // Rows past the end re-read this group's last live row and their accumulators are never stored,
+  // so loads and steps are unconditional; and the loop is software-pipelined by hand: the G loads
+  // of iteration i+1 are issued before iteration i is folded. ptxas otherwise sinks every load of
+  // the 8-byte types down to its first use (load, add, load, add ... -- G dependent round trips
+  // per iteration, 0.45 of the roofline for f64 rows of 256), and neither unconditional loads nor
+  // a warp barrier between the phases talks it out of that.
+  const int last_live = n_live - 1;
+  int r = tr * VEC;
+  if constexpr (!NxcFoldPipe<P>::v) {
+    for (; n_live > 0 && r < R; r += step, p += pstep) {
+      S v[G][VEC];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const S *pg = p + (int64_t)(g < n_live ? g : last_live) * gstep;
+        if (VEC > 1) nxc_load_vec<S, VEC>(pg, v[g]);
+        else v[g][0] = *pg;
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) nxc_step_many<P, VEC>(accg[g], v[g], r, 1);
+    }
+  } else if (n_live > 0 && r < R) {
+    S cur[G][VEC], nxt[G][VEC];
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      if (g < n_live) {
-        if (VEC > 1) nxc_load_vec<S, VEC>(p + g * gstep, v[g]);
-        else v[g][0] = p[g * gstep];
-      }
+      const S *pg = p + (int64_t)(g < n_live ? g : last_live) * gstep;
+      if (VEC > 1) nxc_load_vec<S, VEC>(pg, cur[g]);
+      else cur[g][0] = *pg;
     }
+    for (;;) {
+      const int rn = r + step;
+      const bool more = rn < R;
+      if (more) {
+        p += pstep;
 #pragma unroll
-    for (int g = 0; g < G; g++)
-      if (g < n_live) nxc_step_many<P, VEC>(accg[g], v[g], r, 1);
+        for (int g = 0; g < G; g++) {
+          const S *pg = p + (int64_t)(g < n_live ? g : last_live) * gstep;
+          if (VEC > 1) nxc_load_vec<S, VEC>(pg, nxt[g]);
+          else nxt[g][0] = *pg;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) nxc_step_many<P, VEC>(accg[g], cur[g], r, 1);
+      if (!more) break;
+#pragma unroll
+      for (int g = 0; g < G; g++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) cur[g][e] = nxt[g][e];
+      r = rn;
+    }
   }
 #pragma unroll
   for (int g = 0; g < G; g++) {

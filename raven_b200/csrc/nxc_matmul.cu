@@ -51,9 +51,20 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
     p.b = (const char *)B->data + B->offset * es;
     p.c = (char *)C->data + C->offset * es;
 
-    const bool tc_dtype = (dt == NXC_BF16 || dt == NXC_F16 || (dt == NXC_F32 && ctx->matmul_tf32));
+    const bool tc_dtype = (dt == NXC_BF16 || dt == NXC_F16 || (dt == NXC_F32 && ctx->matmul_tf32 == 1));
     if (tc_dtype) {
       s = nxc_matmul_tc(ctx, p);
+      if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
+    }
+    // f32 at f32-class accuracy on the tensor cores (3xTF32, nxc_matmul_x3.cu) -- the default for
+    // f32 once the product is a few GFLOP and so worth the two split passes (measured 8192^3: 230
+    // vs 30 TFLOP/s; error 2e-6 .. 6e-5 of max |A||B| for K = 1024 .. 8192, inside the classical
+    // K*u sgemm bound and 20x inside the reference's own f32 matmul tolerance, 1e-3 rel + 1e-3 abs,
+    // backend_c/test/matmul_test.ml:831). Mode "ieee" keeps every f32 product on the CUDA-core
+    // kernel (each product and sum rounded to nearest, like the reference's microkernel).
+    if (dt == NXC_F32 && (ctx->matmul_tf32 == 0 || ctx->matmul_tf32 == 2) && p.m >= 128 && p.n >= 128 &&
+        2.0 * (double)p.m * (double)p.n * (double)p.k * (double)p.nbatch >= 2147483648.0) {
+      s = nxc_matmul_f32x3(ctx, p);
       if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
     }
     s = nxc_matmul_simt(ctx, p);

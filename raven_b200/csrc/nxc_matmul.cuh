@@ -21,3 +21,6 @@ nxc_status nxc_matmul_simt(nxc_ctx *ctx, const NxcMatmulProblem &p);
 // the caller then packs the operands and retries, or uses the SIMT path.
 #define NXC_MM_TC_DECLINED ((nxc_status) "tc:declined")
 nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &p);
+// f32 operands split into tf32 hi / lo parts and multiplied as one tf32 GEMM over a tripled K
+// axis (nxc_matmul_x3.cu): f32-class accuracy at tensor-core speed. May decline like the above.
+nxc_status nxc_matmul_f32x3(nxc_ctx *ctx, const NxcMatmulProblem &p);

@@ -68,6 +68,7 @@ struct TcParams {
   int out_bf16;           // 16-bit flavour
   int vec_store;          // rows of C are 16-byte aligned
   int group;              // M-blocks per rasterisation group
+  int kskew;              // concurrent tiles start their K loop up to kskew-1 blocks apart (1 = in lockstep)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -312,7 +313,14 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tile_coords(p, t, bi, mb, nb);
         const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * BLOCK_N + (int)rank * C::B_ROWS;
         const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
-        for (int kb = 0; kb < p.num_kb; kb++) {
+        // Tiles that run concurrently walk K in lockstep otherwise: with a power-of-two row pitch
+        // (K = 16384 bf16: 32 KB) every CTA then asks for the same 128-byte column of its rows,
+        // which lands on a handful of L2 slices / HBM channels. Starting each tile a few k-blocks
+        // apart spreads the columns in flight; the window stays small so panels shared through
+        // L2 are still hit while hot. The accumulation order is a rotation of 0..num_kb-1.
+        const int kb0 = (int)(t % p.kskew);
+        for (int kbi = 0; kbi < p.num_kb; kbi++) {
+          const int kb = kbi + kb0 < p.num_kb ? kbi + kb0 : kbi + kb0 - p.num_kb;
           mbar_wait(&empty[stage], phase ^ 1);
           // PAIR: one arrival (the leader's) and the bytes of BOTH CTAs complete the leader's barrier
           if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * STAGE_BYTES);
@@ -555,6 +563,9 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.a_batched = a_b; p.b_batched = b_b;
   p.group = 8;
   if (const char *f = getenv("NX_CUDA_MM_GROUP")) p.group = atoi(f) > 0 ? atoi(f) : 8;
+  p.kskew = 1;
+  if (const char *f = getenv("NX_CUDA_MM_KSKEW")) p.kskew = atoi(f) > 0 ? atoi(f) : 1;
+  if (p.kskew > p.num_kb) p.kskew = p.num_kb > 0 ? p.num_kb : 1;
   p.out_f32 = (q.dt == NXC_F32);
   p.out_bf16 = (q.dt == NXC_BF16);
   p.vec_store = (((uintptr_t)q.c & 15) == 0) && ((q.c_rs * esize) % 16 == 0) && ((c_bs * esize) % 16 == 0);

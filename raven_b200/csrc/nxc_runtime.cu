@@ -58,7 +58,7 @@ extern "C" nxc_status nxc_ctx_create_on(int device, void *cuda_stream, nxc_ctx *
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   const char *mm = getenv("NX_CUDA_MATMUL");
-  ctx->matmul_tf32 = (mm && strcmp(mm, "tf32") == 0) ? 1 : 0;
+  ctx->matmul_tf32 = (mm && strcmp(mm, "tf32") == 0) ? 1 : (mm && strcmp(mm, "ieee") == 0) ? 3 : 0;
   ctx->rank = 0;
   ctx->world = 1;
   // TMA descriptor encoder: resolved through the runtime so the library has no
@@ -151,6 +151,8 @@ extern "C" uint64_t nxc_launch_count(nxc_ctx *ctx) { return ctx->launches; }
 extern "C" int nxc_set_matmul_mode(nxc_ctx *ctx, const char *mode) {
   if (strcmp(mode, "tf32") == 0) { ctx->matmul_tf32 = 1; return 0; }
   if (strcmp(mode, "f32") == 0) { ctx->matmul_tf32 = 0; return 0; }
+  if (strcmp(mode, "f32x3") == 0) { ctx->matmul_tf32 = 2; return 0; }
+  if (strcmp(mode, "ieee") == 0) { ctx->matmul_tf32 = 3; return 0; }
   return -1;
 }
 

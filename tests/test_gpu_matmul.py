@@ -176,3 +176,45 @@ def test_matmul_tc_tile_modes(ctx, oracle, dtype, pair_mode):
             assert float(np.max(np.abs(got - want))) <= tol * (float(np.max(np.abs(want))) or 1.0), f"batched/{dtype}"
     finally:
         ctx.set_matmul_mode("f32")
+
+
+def test_matmul_f32_large_runs_as_3xtf32_and_keeps_f32_accuracy(ctx, oracle):
+    """f32 products of >= 2 GFLOP take the tensor-core 3xTF32 path (nxc_matmul_x3.cu) by default.
+    Against the reference binary's f32 result: 2e-5 of max (|A||B|) -- far inside the reference's own
+    f32 tolerance (1e-3 rel + 1e-3 abs, backend_c/test/matmul_test.ml:831) and 50x tighter than plain
+    tf32 gets; mode "ieee" pins the CUDA-core kernel and agrees to 2e-6. Transposed views, a K that
+    is not a multiple of the k-block, batch broadcast, and an inf operand (no NaN from inf - inf)."""
+    rng = np.random.default_rng(11)
+    m, k, n = 512, 2056, 1024
+    A = rng.standard_normal((m, k)).astype(np.float32)
+    Bm = rng.standard_normal((k, n)).astype(np.float32)
+    a = H.HostView(A.reshape(-1).copy(), "f32", [m, k])
+    b = H.HostView(Bm.reshape(-1).copy(), "f32", [k, n])
+    at = H.HostView(np.ascontiguousarray(A.T).reshape(-1), "f32", [k, m]).permute([1, 0])
+    bt = H.HostView(np.ascontiguousarray(Bm.T).reshape(-1), "f32", [n, k]).permute([1, 0])
+    want = oracle.matmul(a, b).numpy().astype(np.float64)
+    bound = float((np.abs(A).astype(np.float64) @ np.abs(Bm).astype(np.float64)).max())
+    before = ctx.launch_count()
+    for name, (x, y) in {"nn": (a, b), "tn": (at, b), "nt": (a, bt), "tt": (at, bt)}.items():
+        got = H.download(B.matmul(H.upload(ctx, x), H.upload(ctx, y))).astype(np.float64)
+        assert np.abs(got - want).max() <= 2e-5 * bound, name
+    assert ctx.launch_count() - before >= 4 * 3  # two split passes + the GEMM per product
+    try:
+        ctx.set_matmul_mode("ieee")
+        got = H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, bt))).astype(np.float64)
+        assert np.abs(got - want).max() <= 2e-6 * bound
+    finally:
+        ctx.set_matmul_mode("f32")
+    # batched A [3, m, k] against a broadcast B [k, n]
+    A3 = rng.standard_normal((3, m, k)).astype(np.float32)
+    a3 = H.HostView(A3.reshape(-1).copy(), "f32", [3, m, k])
+    want3 = oracle.matmul(a3, b).numpy().astype(np.float64)
+    got3 = H.download(B.matmul(H.upload(ctx, a3), H.upload(ctx, b))).astype(np.float64)
+    assert got3.shape == (3, m, n) and np.abs(got3 - want3).max() <= 2e-5 * bound * 1.5
+    # an infinite element gives inf in its row, not NaN
+    Ai = A.copy()
+    Ai[7, 5] = np.inf
+    gi = H.download(B.matmul(H.upload(ctx, H.HostView(Ai.reshape(-1), "f32", [m, k])), H.upload(ctx, b)))
+    wi = oracle.matmul(H.HostView(Ai.reshape(-1), "f32", [m, k]), b).numpy()
+    assert np.array_equal(np.isinf(gi), np.isinf(wi)) and np.array_equal(np.isnan(gi), np.isnan(wi))
+    assert np.array_equal(np.sign(gi[7]), np.sign(wi[7]))

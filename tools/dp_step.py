@@ -119,9 +119,12 @@ for _ in range(3):
 if world > 1:
     td.barrier()
 torch.cuda.synchronize()
-reps, tot, comp, exch = 8, 0.0, 0.0, 0.0
+import time
+reps, tot, comp, exch, host = 8, 0.0, 0.0, 0.0, 0.0
 for _ in range(reps):
+    t0 = time.perf_counter()
     loss = step(timed=True)
+    host += (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
     tot += ev[0].elapsed_time(ev[3])
     comp += ev[0].elapsed_time(ev[1])
@@ -136,7 +139,7 @@ if rank == 0:
     print(json.dumps({"workload": f"DP MLP step: {LAYERS}x{WIDTH}, per-GPU batch {BATCH}, {dt.name}, grad allreduce "
                                   f"of {nparams} params ({nparams * dt.itemsize / 1e6:.0f} MB) + SGD",
                       "n_gpus": world, "ms_per_step": round(ms, 3), "samples_per_s": round(world * BATCH / (ms * 1e-3), 1),
-                      "grad_ms": round(comp / reps, 3), "exchange_ms": round(exch / reps, 3),
+                      "grad_ms": round(comp / reps, 3), "host_issue_ms": round(host / reps, 3), "exchange_ms": round(exch / reps, 3),
                       "exchange": "bucketed allreduce on the comm stream under the backward pass" if OVERLAP
                       else "allreduce after the backward pass", "scaling": "weak"}))
 if comm is not None:

@@ -32,27 +32,29 @@ def rand(dt, n):
     return t
 
 
-a = rand(D.float32, n)
-b = rand(D.float32, n)
+DT = D.of(os.environ.get("FOLD_CASES_DT", "f32"))
+ES = DT.itemsize
+a = rand(DT, n)
+b = rand(DT, n)
 short = B.reshape(a, [n // 256, 256])
 sq = B.reshape(a, [1 << (lg // 2), n >> (lg // 2)])
 bs = B.reshape(b, [1 << (lg // 2), n >> (lg // 2)])
 r, c = sq.shape
 cases = {
-    "sum inner [N/256,256]": (lambda: B.reduce(short, "sum", [1]), 4 * n),
-    "max inner [N/256,256]": (lambda: B.reduce(short, "max", [1]), 4 * n),
-    "argmax inner [N/256,256]": (lambda: B.argmax(short, 1), 4 * n),
-    "sum outer [N/256,256]": (lambda: B.reduce(short, "sum", [0]), 4 * n),
-    "argmax outer [N/256,256]": (lambda: B.argmax(short, 0), 4 * n),
-    "argmax outer sqrt": (lambda: B.argmax(sq, 0), 4 * n),
-    "argmax inner sqrt": (lambda: B.argmax(sq, 1), 4 * n),
-    "max outer sqrt": (lambda: B.reduce(sq, "max", [0]), 4 * n),
-    "add col-broadcast": (lambda: B.add(sq, B.expand(B.shrink(bs, [(0, r), (0, 1)]), [r, c])), 8 * n),
-    "add row-broadcast": (lambda: B.add(sq, B.expand(B.shrink(bs, [(0, 1), (0, c)]), [r, c])), 8 * n),
-    "add flipped": (lambda: B.add(sq, B.flip(bs, [True, True])), 12 * n),
-    "add transposed": (lambda: B.add(sq, B.permute(B.reshape(b, [c, r]), [1, 0])), 12 * n),
-    "contiguous(transpose)": (lambda: B.contiguous(B.permute(sq, [1, 0])), 8 * n),
-    "sub rowmax [N/256,256]-[N/256,1]": (lambda: B.sub(short, B.expand(B.shrink(short, [(0, n // 256), (0, 1)]), [n // 256, 256])), 8 * n),
+    "sum inner [N/256,256]": (lambda: B.reduce(short, "sum", [1]), ES * n),
+    "max inner [N/256,256]": (lambda: B.reduce(short, "max", [1]), ES * n),
+    "argmax inner [N/256,256]": (lambda: B.argmax(short, 1), ES * n),
+    "sum outer [N/256,256]": (lambda: B.reduce(short, "sum", [0]), ES * n),
+    "argmax outer [N/256,256]": (lambda: B.argmax(short, 0), ES * n),
+    "argmax outer sqrt": (lambda: B.argmax(sq, 0), ES * n),
+    "argmax inner sqrt": (lambda: B.argmax(sq, 1), ES * n),
+    "max outer sqrt": (lambda: B.reduce(sq, "max", [0]), ES * n),
+    "add col-broadcast": (lambda: B.add(sq, B.expand(B.shrink(bs, [(0, r), (0, 1)]), [r, c])), 2 * ES * n),
+    "add row-broadcast": (lambda: B.add(sq, B.expand(B.shrink(bs, [(0, 1), (0, c)]), [r, c])), 2 * ES * n),
+    "add flipped": (lambda: B.add(sq, B.flip(bs, [True, True])), 3 * ES * n),
+    "add transposed": (lambda: B.add(sq, B.permute(B.reshape(b, [c, r]), [1, 0])), 3 * ES * n),
+    "contiguous(transpose)": (lambda: B.contiguous(B.permute(sq, [1, 0])), 2 * ES * n),
+    "sub rowmax [N/256,256]-[N/256,1]": (lambda: B.sub(short, B.expand(B.shrink(short, [(0, n // 256), (0, 1)]), [n // 256, 256])), 2 * ES * n),
 }
 timing = os.environ.get("FOLD_CASES_TIME") == "1"
 res = {}

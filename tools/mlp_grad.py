@@ -89,7 +89,10 @@ out = {"workload": f"Rune.grad-shaped MLP replay: {LAYERS} layers x {WIDTH}, bat
 out["bf16"] = run(D.bfloat16)
 ctx.set_matmul_mode("tf32")
 out["f32_tf32"] = run(D.float32)
+ctx.set_matmul_mode("f32")   # the default: f32-class accuracy, large products as 3xTF32 on the tensor cores
+out["f32_default_3xtf32"] = run(D.float32)
 if os.environ.get("MLP_EXACT", "0") == "1":
+    ctx.set_matmul_mode("ieee")
+    out["f32_ieee_cuda_cores"] = run(D.float32)
     ctx.set_matmul_mode("f32")
-    out["f32_exact"] = run(D.float32)
 print(json.dumps(out))

@@ -105,11 +105,11 @@ for dt in (D.float32, D.float64, D.int32):
         del a, b, A, Bm
 
 if os.environ.get("SWEEP_MATMUL", "1") == "1":
-    for dtn, mode in (("bf16", None), ("f16", None), ("f32", "tf32"), ("f32", "f32")):
+    for dtn, mode in (("bf16", None), ("f16", None), ("f32", "tf32"), ("f32", "f32"), ("f32", "ieee")):
         dt = D.of(dtn)
         ctx.set_matmul_mode(mode or "f32")
         for M in (512, 1024, 2048, 4096, 8192, 16384):
-            if mode == "f32" and M > 8192:
+            if mode == "ieee" and M > 8192:
                 continue
             src = rand(D.float32, M * M)
             x = B.reshape(src if dt is D.float32 else B.cast(src, dt), [M, M])
