@@ -57,9 +57,17 @@ template <int OP, int DT> struct RedP {
         else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
         return r;
       } else {
-        if (a != a) return a;
-        if (b != b) return b;
-        return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
+        // no max.NaN for f64: branch-free all the same -- the IEEE max / min (which drops a NaN),
+        // the sum (NaN iff either is), and one unordered compare choosing between them; the
+        // branchy form (test a, test b, compare, select) held short f64 rows at 0.63 of the roofline
+        double r;
+        if (OP == NXC_RMAX)
+          asm("{ .reg .pred p; .reg .f64 m, s; max.f64 m, %1, %2; add.f64 s, %1, %2; setp.nan.f64 p, %1, %2; "
+              "selp.f64 %0, s, m, p; }" : "=d"(r) : "d"(a), "d"(b));
+        else
+          asm("{ .reg .pred p; .reg .f64 m, s; min.f64 m, %1, %2; add.f64 s, %1, %2; setp.nan.f64 p, %1, %2; "
+              "selp.f64 %0, s, m, p; }" : "=d"(r) : "d"(a), "d"(b));
+        return r;
       }
     } else {
       return OP == NXC_RMAX ? (b > a ? b : a) : (b < a ? b : a);
