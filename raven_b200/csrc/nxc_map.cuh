@@ -202,14 +202,19 @@ nxc_map_flat_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__re
 // 72 % of the stall samples sat on the broadcast moves) -- nxc_item_elem picks the element at
 // compute time instead.
 template <typename S, int VW>
-__device__ __forceinline__ void nxc_load_item(const S *p, bool bcast, bool neg, S (&r)[VW]) {
-  if (VW == 1 || bcast) r[0] = *p;
+__device__ __forceinline__ void nxc_load_item(const S *p, bool bcast, bool neg, S (&r)[VW], S &sc) {
+  // A broadcast element gets a register of its OWN: sharing r[0] between the scalar and the vector
+  // load makes ptxas merge the two predicated destinations with a move placed right behind the load
+  // -- for the 8-byte types that put one dependent round trip per slot back (ncu, f64
+  // [R,C]+[R,1]: four moves with 20 % of the stall samples each, 0.77 of the roofline).
+  if (VW == 1) r[0] = *p;
+  else if (bcast) sc = *p;
   else nxc_load_vec<S, VW>(neg ? p - (VW - 1) : p, r);
 }
 template <typename S, int VW>
-__device__ __forceinline__ S nxc_item_elem(const S (&r)[VW], int i, bool bcast, bool neg) {
+__device__ __forceinline__ S nxc_item_elem(const S (&r)[VW], const S &sc, int i, bool bcast, bool neg) {
   if (VW == 1) return r[0];
-  return bcast ? r[0] : (neg ? r[VW - 1 - i] : r[i]);
+  return bcast ? sc : (neg ? r[VW - 1 - i] : r[i]);
 }
 
 // row -> element offsets of the first NEED operands (the outer coordinates' contribution)
@@ -261,6 +266,7 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
   const uint32_t rb = nxc_fastdiv(blockIdx.x, args.chunks_div);
   const uint32_t chunk = blockIdx.x - rb * args.chunks;
   S1 va[U][VW]; S2 vb[U][VW]; S3 vc[U][VW];
+  S1 xa[U]; S2 xb[U]; S3 xc[U];  // broadcast elements (see nxc_load_item)
   const bool ba = args.bcast_mask & 2u, bb = args.bcast_mask & 4u, bc = args.bcast_mask & 8u;
   const bool na = args.neg_mask & 2u, nb = args.neg_mask & 4u, nc = args.neg_mask & 8u;
   // the 4 slots of a thread are a constant pointer step apart (TX items along the row, or TY
@@ -299,14 +305,34 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
     n_live = -1;
   }
   if (!ROWS || n_live >= 0) {
+    // Load phase: nothing predicated. Slots past the end re-load the last live slot (their results
+    // are never stored) and the broadcast pattern, uniform over the grid, picks one of a few
+    // straight-line variants by a real branch. With `@p LDG` forms ptxas funnels the 8-byte types'
+    // vector loads through one register quad and copies each result out right behind its load --
+    // one dependent round trip per slot (ncu, f64 [R,C]+[R,1]: 0.77 of the roofline, four moves
+    // holding 20 % of the stall samples each).
+    auto load_all = [&](auto BA, auto BB, auto BC) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (u < n_live) {
-        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, ba, na, va[u]);
-        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, bb, nb, vb[u]);
-        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, bc, nc, vc[u]);
+      for (int u = 0; u < U; u++) {
+        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, decltype(BA)::value, na, va[u], xa[u]);
+        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, decltype(BB)::value, nb, vb[u], xb[u]);
+        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, decltype(BC)::value, nc, vc[u], xc[u]);
+        if (u + 1 < n_live) { pa += sa; pb += sb; pc += sc; }
       }
-      pa += sa; pb += sb; pc += sc;
+    };
+    typedef std::integral_constant<bool, false> F_;
+    typedef std::integral_constant<bool, true> T_;
+    if (!(ba | bb | bc)) load_all(F_(), F_(), F_());
+    else if (bb && !ba && !bc) load_all(F_(), T_(), F_());
+    else if (ba && !bb && !bc) load_all(T_(), F_(), F_());
+    else {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, ba, na, va[u], xa[u]);
+        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, bb, nb, vb[u], xb[u]);
+        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, bc, nc, vc[u], xc[u]);
+        if (u + 1 < n_live) { pa += sa; pb += sb; pc += sc; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -314,8 +340,8 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
         S0 vo[VW];
 #pragma unroll
         for (int i = 0; i < VW; i++)
-          vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], i, bb, nb),
-                         nxc_item_elem<S3, VW>(vc[u], i, bc, nc), prm);
+          vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], xb[u], i, bb, nb),
+                         nxc_item_elem<S3, VW>(vc[u], xc[u], i, bc, nc), prm);
         if (VW == 1) po[0] = vo[0];
         else nxc_store_vec<S0, VW>(po, vo);
       }
@@ -333,14 +359,14 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
         if (row >= args.rows) break;
         int64_t off[NOP];
         nxc_row_offsets<NOP, NOP>(args, row, off);
-        if (K::NIN >= 1) nxc_load_item<S1, VW>(a + off[KA] + item * args.inner_stride[KA], args.bcast_mask & 2u, args.neg_mask & 2u, va[0]);
-        if (K::NIN >= 2) nxc_load_item<S2, VW>(b + off[KB] + item * args.inner_stride[KB], args.bcast_mask & 4u, args.neg_mask & 4u, vb[0]);
-        if (K::NIN >= 3) nxc_load_item<S3, VW>(c + off[KC] + item * args.inner_stride[KC], args.bcast_mask & 8u, args.neg_mask & 8u, vc[0]);
+        if (K::NIN >= 1) nxc_load_item<S1, VW>(a + off[KA] + item * args.inner_stride[KA], args.bcast_mask & 2u, args.neg_mask & 2u, va[0], xa[0]);
+        if (K::NIN >= 2) nxc_load_item<S2, VW>(b + off[KB] + item * args.inner_stride[KB], args.bcast_mask & 4u, args.neg_mask & 4u, vb[0], xb[0]);
+        if (K::NIN >= 3) nxc_load_item<S3, VW>(c + off[KC] + item * args.inner_stride[KC], args.bcast_mask & 8u, args.neg_mask & 8u, vc[0], xc[0]);
         S0 vo[VW];
 #pragma unroll
         for (int i = 0; i < VW; i++)
-          vo[i] = K::run(nxc_item_elem<S1, VW>(va[0], i, ba, na), nxc_item_elem<S2, VW>(vb[0], i, bb, nb),
-                         nxc_item_elem<S3, VW>(vc[0], i, bc, nc), prm);
+          vo[i] = K::run(nxc_item_elem<S1, VW>(va[0], xa[0], i, ba, na), nxc_item_elem<S2, VW>(vb[0], xb[0], i, bb, nb),
+                         nxc_item_elem<S3, VW>(vc[0], xc[0], i, bc, nc), prm);
         S0 *q = out + off[0] + item * args.inner_stride[0];
         if (VW == 1) q[0] = vo[0];
         else nxc_store_vec<S0, VW>(q, vo);
