@@ -128,6 +128,7 @@ template <int IS_MAX, int DT> struct ArgP {
   }
   __device__ __forceinline__ static SO finish(A a) { return a.idx < 0 ? 0 : a.idx; }
 };
+template <int IS_MAX, int DT> struct NxcFoldFewLanes<ArgP<IS_MAX, DT>> { static constexpr bool v = true; };
 template <int IS_MAX, int DT> struct NxcFoldPipe<ArgP<IS_MAX, DT>> {
   static constexpr bool v = sizeof(typename ArgP<IS_MAX, DT>::S) >= 8;
 };

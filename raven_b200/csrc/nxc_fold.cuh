@@ -123,6 +123,10 @@ template <class P> struct NxcFoldG { static constexpr int v = sizeof(typename P:
 // Needed for the 8-byte types (see the kernel); it doubles the registers holding loaded values, so
 // policies whose fold step is itself heavy (argreduce on 4-byte types) opt out and keep 4 CTAs/SM.
 template <class P> struct NxcFoldPipe { static constexpr bool v = true; };
+// short-row path: prefer few lanes per row (8 work items each) when rows are plentiful? Pays when the
+// per-row epilogue is heavy (argreduce's index vote, the f64 NaN-propagating max); costs the cheap
+// f32 sum / max 7 % (a warp's load then spans 4 rows instead of one contiguous 512 bytes).
+template <class P> struct NxcFoldFewLanes { static constexpr bool v = false; };
 
 // offsets of output `o`: one kept dim (the usual [rows, R] case) is a multiplication, not a
 // decode -- cheap enough to redo at the store instead of keeping per-row offsets in registers
@@ -625,6 +629,15 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   // plenty of rows: keep a row inside one warp (shuffle-only combine, no block barrier) and let
   // each lane walk the row; many threads per row only pay off when rows are scarce
   if (tl > 5 && items <= 512 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
+  // ... and with rows to spare, fewer lanes per row, 8 work items each: the per-row epilogue (a
+  // shuffle butterfly, for argreduce also the index vote) is paid per thread GROUP, and at 32 lanes
+  // per 256-element row it was a quarter of the argmax kernel's instructions. Not below 8 lanes:
+  // a group's load stays a full 128-byte line.
+  if (NxcFoldFewLanes<P>::v && items <= 512 && p.nr <= 1 && p.nk <= 1 && p.O >= (int64_t)ctx->sm_count * 2048) {
+    int want = nxc_log2_ceil(items) - 3;
+    if (want < 3) want = 3;
+    if (want < tl) tl = want;
+  }
   a.tpr_log2 = tl;
   const int RPB = NXC_FOLD_THREADS >> tl;
   a.G = (tl < 8 && p.nr <= 1 && p.nk <= 1 && p.R < 0x7FFFFFFFLL && p.O >= (int64_t)RPB * NxcFoldG<P>::v * ctx->sm_count) ? NxcFoldG<P>::v : 1;

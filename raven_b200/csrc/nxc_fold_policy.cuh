@@ -77,6 +77,11 @@ template <int OP, int DT> struct RedP {
 };
 
 
+template <int OP, int DT> struct NxcFoldFewLanes<RedP<OP, DT>> {
+  static constexpr bool v = (OP == NXC_RMAX || OP == NXC_RMIN) && sizeof(typename RedP<OP, DT>::S) == 8 &&
+                            RedP<OP, DT>::cls == NXC_CLS_FLOAT;
+};
+
 nxc_status nxc_reduce_sumprod(nxc_ctx *ctx, int op, int dt, const NxcFoldPlan &p);
 nxc_status nxc_reduce_maxmin(nxc_ctx *ctx, int op, int dt, const NxcFoldPlan &p);
 

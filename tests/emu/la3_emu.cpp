@@ -59,3 +59,26 @@ extern "C" int la3_emu_eig(const double *a, int64_t n, int vectors, double *w, d
   free(h); free(z); free(x); free(vs); free(rs); free(rc);
   return status;
 }
+
+template <class T>
+static int eigh_run(const T *a, int64_t n, int vectors, double *w, T *v) {
+  T *gt = (T *)calloc((size_t)(n * n + 1), sizeof(T));
+  T *vt = (T *)calloc((size_t)(n * n + 1), sizeof(T));
+  double *sg = (double *)calloc((size_t)n + 1, sizeof(double));
+  int *rk = (int *)calloc((size_t)n + 1, sizeof(int));
+  double red[1];
+  int flags[2] = {0, 0}, status = 0;
+  La3Thr t = {0, 1, 0, 1, 0, 1};
+  la3_eigh_body<T>(t, a, gt, vt, v, w, sg, rk, red, flags, n, vectors, 60, &status);
+  free(gt); free(vt); free(sg); free(rk);
+  return status;
+}
+
+extern "C" int la3_emu_eigh(int cdt, const void *a, int64_t n, int vectors, double *w, void *v) {
+  switch (cdt) {
+    case 0: return eigh_run<float>((const float *)a, n, vectors, w, (float *)v);
+    case 1: return eigh_run<double>((const double *)a, n, vectors, w, (double *)v);
+    case 2: return eigh_run<La3C32>((const La3C32 *)a, n, vectors, w, (La3C32 *)v);
+    default: return eigh_run<La3C64>((const La3C64 *)a, n, vectors, w, (La3C64 *)v);
+  }
+}

@@ -47,6 +47,7 @@ def rand(shape, dt):
 
 rows = []
 skews = [int(x) for x in os.environ.get("KSKEWS", "1,4,8,16,32").split(",")]
+groups = [int(x) for x in os.environ.get("MM_GROUPS", "").split(",") if x]
 for M in (4096, 8192, 16384):
     x, y = rand([M, M], D.bfloat16), rand([M, M], D.bfloat16)
     lays = {"NN": (x, y), "NT": (x, B.permute(y, [1, 0])), "TN": (B.permute(x, [1, 0]), y)}
@@ -56,6 +57,12 @@ for M in (4096, 8192, 16384):
             os.environ["NX_CUDA_MM_KSKEW"] = str(ks)
             ms = timeit(lambda: B.matmul(p, q))
             r[f"skew{ks}_tflops"] = round(2.0 * M ** 3 / (ms * 1e-3) / 1e12, 1)
+        os.environ["NX_CUDA_MM_KSKEW"] = "1"
+        for g in groups:   # M-blocks per rasterisation group (L2 reuse of the B panels)
+            os.environ["NX_CUDA_MM_GROUP"] = str(g)
+            ms = timeit(lambda: B.matmul(p, q))
+            r[f"group{g}_tflops"] = round(2.0 * M ** 3 / (ms * 1e-3) / 1e12, 1)
+        os.environ.pop("NX_CUDA_MM_GROUP", None)
         rows.append(r)
         print(r, file=sys.stderr)
     del x, y, lays
