@@ -4,6 +4,75 @@
 // (shape/aliased -> Invalid_argument; dtype mismatch / unsupported -> Failure).
 #include "nxc_matmul.cuh"
 
+// The tensor-core kernel feeds on TMA, which wants a unit stride on one matrix dim, 16-byte multiples
+// on every other stride and a 16-byte aligned base. A view that cannot be described that way (a row
+// pitch of 50257 bf16 -- GPT-2's vocabulary -- a sliced or doubly strided operand, a batch that does
+// not collapse) is PACKED: one pass through the backend's own strided copy into a K-major buffer
+// with an aligned pitch, then the same kernel. One extra read + write of the operand (HBM-bound)
+// against a CUDA-core GEMM 30-40x slower than the tensor cores.
+static bool nxc_mm_operand_ok(const char *base, int64_t rs, int64_t cs, int64_t rows, int64_t cols, int esize) {
+  const int64_t al = 16 / esize;
+  if (((uintptr_t)base & 15) != 0) return false;
+  if (cs == 1 || cols == 1) return rs > 0 && rs % al == 0;
+  if (rs == 1 || rows == 1) return cs > 0 && cs % al == 0;
+  return false;
+}
+
+static nxc_status nxc_matmul_tc_packed(nxc_ctx *ctx, const NxcMatmulProblem &q) {
+  const int esize = (q.dt == NXC_F32) ? 4 : 2;
+  const int64_t al = 16 / esize;
+  if (q.k == 0 || q.c_cs != 1 || q.m * q.n * q.k < ((int64_t)1 << 24)) return NXC_MM_TC_DECLINED;
+  bool a_b = false, b_b = false, bad_batch = false;
+  for (int i = 0; i < q.batch_nd; i++) {
+    if (q.bshape[i] > 1 && q.as_[i] != 0) a_b = true;
+    if (q.bshape[i] > 1 && q.bs_[i] != 0) b_b = true;
+    if (q.bshape[i] > 1 && ((q.as_[i] % al) != 0 || (q.bs_[i] % al) != 0)) bad_batch = true;
+  }
+  // (a batch that does not collapse to one stride is also a reason to pack; detecting it here would
+  // repeat the kernel's own walk, so any decline of a large product packs whatever is batched)
+  const bool pack_a = bad_batch || a_b || !nxc_mm_operand_ok(q.a, q.a_rs, q.a_cs, q.m, q.k, esize);
+  const bool pack_b = bad_batch || b_b || !nxc_mm_operand_ok(q.b, q.b_cs, q.b_rs, q.n, q.k, esize);
+  if (!pack_a && !pack_b) return NXC_MM_TC_DECLINED;  // declined for another reason: nothing to gain
+  const int64_t kp = (q.k + al - 1) / al * al;
+  NxcMatmulProblem p = q;
+  void *pa = NULL, *pb = NULL;
+  nxc_status s = NXC_OK;
+  auto pack = [&](const char *src, int64_t rows, int64_t rs, int64_t ks, const int64_t *bstr, bool batched, void **out,
+                  int64_t *new_bstr) -> nxc_status {
+    const int64_t nb = batched ? q.nbatch : 1;
+    nxc_status st = nxc_alloc(ctx, (size_t)(nb * rows * kp) * (size_t)esize, out);
+    if (st) return st;
+    nxc_tensor d, x;
+    d.data = *out; x.data = (void *)src;
+    d.dtype = x.dtype = q.dt;
+    d.offset = x.offset = 0;
+    int nd = 0;
+    int64_t ext = 1;
+    if (batched) {
+      for (int i = 0; i < q.batch_nd; i++) { d.shape[nd] = x.shape[nd] = q.bshape[i]; x.strides[nd] = bstr[i]; nd++; }
+      for (int i = q.batch_nd - 1; i >= 0; i--) { d.strides[i] = ext * rows * kp; new_bstr[i] = q.bshape[i] > 1 ? d.strides[i] : 0; ext *= q.bshape[i]; }
+    } else {
+      for (int i = 0; i < q.batch_nd; i++) new_bstr[i] = 0;
+    }
+    d.shape[nd] = x.shape[nd] = rows; d.strides[nd] = kp; x.strides[nd] = rs; nd++;
+    d.shape[nd] = x.shape[nd] = q.k; d.strides[nd] = 1; x.strides[nd] = ks; nd++;
+    d.ndim = x.ndim = nd;
+    return nxc_copy(ctx, &d, &x);
+  };
+  if (pack_a) {
+    s = pack(q.a, q.m, q.a_rs, q.a_cs, q.as_, a_b, &pa, p.as_);
+    p.a = (const char *)pa; p.a_rs = kp; p.a_cs = 1;
+  }
+  if (!s && pack_b) {
+    s = pack(q.b, q.n, q.b_cs, q.b_rs, q.bs_, b_b, &pb, p.bs_);   // B^T, K-major
+    p.b = (const char *)pb; p.b_rs = 1; p.b_cs = kp;
+  }
+  if (!s) s = nxc_matmul_tc(ctx, p);
+  if (pa) nxc_free(ctx, pa);   // stream-ordered: reused only after the GEMM that reads them
+  if (pb) nxc_free(ctx, pb);
+  return s;
+}
+
 extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_tensor *A,
                                  const nxc_tensor *B) {
   nxc_status s = NXC_OK;
@@ -54,6 +123,7 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
     const bool tc_dtype = (dt == NXC_BF16 || dt == NXC_F16 || (dt == NXC_F32 && ctx->matmul_tf32 == 1));
     if (tc_dtype) {
       s = nxc_matmul_tc(ctx, p);
+      if (s == NXC_MM_TC_DECLINED) s = nxc_matmul_tc_packed(ctx, p);
       if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
     }
     // f32 at f32-class accuracy on the tensor cores (3xTF32, nxc_matmul_x3.cu) -- the default for

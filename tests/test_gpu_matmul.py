@@ -218,3 +218,39 @@ def test_matmul_f32_large_runs_as_3xtf32_and_keeps_f32_accuracy(ctx, oracle):
     wi = oracle.matmul(H.HostView(Ai.reshape(-1), "f32", [m, k]), b).numpy()
     assert np.array_equal(np.isinf(gi), np.isinf(wi)) and np.array_equal(np.isnan(gi), np.isnan(wi))
     assert np.array_equal(np.sign(gi[7]), np.sign(wi[7]))
+
+
+def test_matmul_tensor_core_path_packs_operands_tma_cannot_describe(ctx, oracle):
+    """A row pitch that is not a multiple of 16 bytes (GPT-2's 50257-wide logits gradient), a base
+    that is not 16-byte aligned (a column slice) and a doubly strided view cannot be handed to TMA:
+    large products pack such an operand once (strided copy, K-major, aligned pitch) and still run on
+    the tensor cores -- same result as the reference binary to the bf16 tolerance, and more than the
+    single launch the CUDA-core fallback would be."""
+    rng = np.random.default_rng(12)
+    m, k, n = 384, 512, 1001
+    A = H.to_storage("bf16", rng.standard_normal((m, k)) / 8)
+    Bw = H.to_storage("bf16", rng.standard_normal((k, n + 3)))
+    a = H.HostView(A.reshape(-1).copy(), "bf16", [m, k])
+    b_full = H.HostView(Bw.reshape(-1).copy(), "bf16", [k, n + 3])
+    cases = {
+        "odd pitch": (a, H.HostView(np.ascontiguousarray(Bw[:, :n]).reshape(-1), "bf16", [k, n])),
+        "column slice (misaligned base, odd pitch)": (a, b_full.shrink([(0, k), (1, n + 1)])),
+        "odd-pitch lhs through a transposed view": (
+            H.HostView(np.ascontiguousarray(A.T[:, :m - 1]).reshape(-1), "bf16", [k, m - 1]).permute([1, 0]),
+            H.HostView(np.ascontiguousarray(Bw[:, :n]).reshape(-1), "bf16", [k, n])),
+    }
+    for name, (x, y) in cases.items():
+        want = oracle.matmul(x, y).numpy()
+        before = ctx.launch_count()
+        got = H.download(B.matmul(H.upload(ctx, x), H.upload(ctx, y)))
+        assert ctx.launch_count() - before >= 2, name
+        scale = float(np.max(np.abs(H.storage_to_float("bf16", want)))) or 1.0
+        H.assert_close("bf16", got, want, rel=_tol("bf16", k), abs_=_tol("bf16", k) * scale, what=name)
+    # batched lhs whose batch stride is not a 16-byte multiple, against a broadcast rhs
+    A3 = H.to_storage("bf16", rng.standard_normal((3, 128, k + 1)) / 8)
+    a3 = H.HostView(A3.reshape(-1).copy(), "bf16", [3, 128, k + 1]).shrink([(0, 3), (0, 128), (0, k)])
+    y = cases["odd pitch"][1]
+    want = oracle.matmul(a3, y).numpy()
+    got = H.download(B.matmul(H.upload(ctx, a3), H.upload(ctx, y)))
+    scale = float(np.max(np.abs(H.storage_to_float("bf16", want)))) or 1.0
+    H.assert_close("bf16", got, want, rel=_tol("bf16", k), abs_=_tol("bf16", k) * scale, what="batched odd pitch")
