@@ -254,3 +254,45 @@ def test_matmul_tensor_core_path_packs_operands_tma_cannot_describe(ctx, oracle)
     got = H.download(B.matmul(H.upload(ctx, a3), H.upload(ctx, y)))
     scale = float(np.max(np.abs(H.storage_to_float("bf16", want)))) or 1.0
     H.assert_close("bf16", got, want, rel=_tol("bf16", k), abs_=_tol("bf16", k) * scale, what="batched odd pitch")
+
+
+def test_matmul_f32_attention_shaped_batch_runs_as_3xtf32(ctx, oracle):
+    """q k^T at GPT-2 shapes with a full-length sequence: [2, 12, 1024, 64] x a transposed VIEW of
+    [2, 12, 1024, 64] -- 3.2 GFLOP, K = 64 (two k-blocks per section), two batch dims that collapse to
+    one stride. Against the reference binary's f32 product."""
+    rng = np.random.default_rng(13)
+    Bt, Hh, T, Dh = 2, 12, 1024, 64
+    q = H.HostView.from_array(rng.standard_normal((Bt, Hh, T, Dh)).astype(np.float32), "f32")
+    k = H.HostView.from_array(rng.standard_normal((Bt, Hh, T, Dh)).astype(np.float32), "f32")
+    kt = k.permute([0, 1, 3, 2])
+    want = oracle.matmul(q, kt).numpy().astype(np.float64)
+    before = ctx.launch_count()
+    got = H.download(B.matmul(H.upload(ctx, q), H.upload(ctx, kt))).astype(np.float64)
+    assert ctx.launch_count() - before == 3
+    bound = float(np.abs(want).max()) * 4
+    assert got.shape == (Bt, Hh, T, T) and np.abs(got - want).max() <= 2e-5 * bound
+
+
+def test_matmul_m_major_lhs_with_wide_n_is_packed_and_bit_identical(ctx):
+    """dW = x^T g shapes: an M-major (transposed-view) left operand with N >= 4096 is transposed once
+    into a K-major buffer before the tensor-core kernel (nxc_matmul.cu). Property check at a size the
+    oracle cannot afford: the result equals, bit for bit, the product of the materialised transpose,
+    and differs in launch count from the in-place route (NX_CUDA_MM_NO_APACK is not set here)."""
+    rng = np.random.default_rng(14)
+    m, k, n = 1024, 4096, 4096
+    xt = B.cast(B.reshape(B.from_host(ctx, rng.standard_normal(k * m).astype(np.float32)), [k, m]), "bf16")   # x: [k, m]
+    g = B.cast(B.reshape(B.from_host(ctx, rng.standard_normal(k * n).astype(np.float32)), [k, n]), "bf16")
+    before = ctx.launch_count()
+    via_view = H.download(B.matmul(B.permute(xt, [1, 0]), g))
+    n_view = ctx.launch_count() - before
+    a = B.contiguous(B.permute(xt, [1, 0]))
+    before = ctx.launch_count()
+    via_copy = H.download(B.matmul(a, g))
+    assert ctx.launch_count() - before == 1 and n_view == 2
+    assert via_view.shape == (m, n) and np.array_equal(via_view, via_copy)
+    # and a spot check of values against float64 on a few rows
+    xf = H.bf16_bits_to_f32(H.download(xt)).astype(np.float64)
+    gf = H.bf16_bits_to_f32(H.download(g)).astype(np.float64)
+    want = xf[:, :4].T @ gf
+    got = H.bf16_bits_to_f32(via_view[:4]).astype(np.float64)
+    assert np.abs(got - want).max() <= 1.6e-2 * np.abs(want).max()
