@@ -45,12 +45,20 @@ constexpr int ROW_BYTES = 128;  // one swizzle row: BLOCK_K * esize
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-template <bool PAIR> struct Cfg {
+template <bool PAIR, bool WIDE = false> struct Cfg {
   static constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;  // rows of C per tile
-  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;  // rows of B (columns of C) this CTA stages
-  static constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;     // 16 / 32 KB
+  // WIDE (PAIR only): a 256 x 512 tile -- two 256-column halves that share the staged A rows, so a
+  // k-block moves 96 KB for twice the flops of the 64 KB a 256 x 256 tile moves (170 instead of 128
+  // flop per L2 byte: the pair kernel is bound by L2 -> SM bandwidth). The price:
+  // the accumulator takes all 512 TMEM columns, so the epilogue no longer overlaps the next tile.
+  static constexpr int TILE_N = WIDE ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int N_HALVES = WIDE ? 2 : 1;
+  static constexpr int NUM_ACC = WIDE ? 1 : 2;
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;  // rows of B per CTA and per half
+  static constexpr int B_HALF_BYTES = B_ROWS * ROW_BYTES;      // 16 / 32 KB
+  static constexpr int B_STAGE_BYTES = N_HALVES * B_HALF_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = PAIR ? 7 : 4;
+  static constexpr int STAGES = PAIR ? (WIDE ? 4 : 7) : 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -253,14 +261,15 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int64_t t, int &b
   nb = rr / gsz;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool WIDE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  void *__restrict__ Cout, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  typedef Cfg<PAIR> C;
+  typedef Cfg<PAIR, WIDE> C;
   constexpr int STAGES = C::STAGES, B_STAGE_BYTES = C::B_STAGE_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int NUM_ACC = C::NUM_ACC;
   uint8_t *smem_a = smem;
   uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);
@@ -311,7 +320,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int64_t t = worker; t < total_tiles; t += nworkers) {
         int bi, mb, nb;
         tile_coords(p, t, bi, mb, nb);
-        const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * BLOCK_N + (int)rank * C::B_ROWS;
+        const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * C::TILE_N + (int)rank * C::B_ROWS;
         const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
         // Tiles that run concurrently walk K in lockstep otherwise: with a power-of-two row pitch
         // (K = 16384 bf16: 32 KB) every CTA then asks for the same 128-byte column of its rows,
@@ -339,12 +348,17 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = 0; j < BLOCK_M / elems_per_row; j++)
               load(&map_a, sa + j * box_bytes, m0 + j * elems_per_row, k0, ba);
           }
-          if (!p.b_mn) {
-            load(&map_b, sb, k0, n0, bb);
-          } else {
-            const int box_bytes = p.block_k * ROW_BYTES;
-            for (int j = 0; j < C::B_ROWS / elems_per_row; j++)
-              load(&map_b, sb + j * box_bytes, n0 + j * elems_per_row, k0, bb);
+#pragma unroll
+          for (int h = 0; h < C::N_HALVES; h++) {  // WIDE: this CTA's 128 columns of each 256-column half
+            uint8_t *sbh = sb + h * C::B_HALF_BYTES;
+            const int nh = n0 + h * BLOCK_N;
+            if (!p.b_mn) {
+              load(&map_b, sbh, k0, nh, bb);
+            } else {
+              const int box_bytes = p.block_k * ROW_BYTES;
+              for (int j = 0; j < C::B_ROWS / elems_per_row; j++)
+                load(&map_b, sbh + j * box_bytes, nh + j * elems_per_row, k0, bb);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -372,7 +386,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (PAIR) mbar_wait_cluster(&tempty[as], aphase ^ 1);
       else mbar_wait(&tempty[as], aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + (uint32_t)as * BLOCK_N;
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * BLOCK_N;  // WIDE: as == 0, both halves side by side
       for (int kb = 0; kb < p.num_kb; kb++) {
         mbar_wait(&full[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -382,14 +396,18 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint64_t ad = make_desc(sa + j * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t bd = make_desc(sb + j * b_kstep, b_lbo, b_sbo, b_lay);
             const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-            if (PAIR) {
-              if (p.esize == 2) umma_f16_pair(tmem_d, ad, bd, p.idesc, acc);
-              else umma_tf32_pair(tmem_d, ad, bd, p.idesc, acc);
-            } else {
-              if (p.esize == 2) umma_f16(tmem_d, ad, bd, p.idesc, acc);
-              else umma_tf32(tmem_d, ad, bd, p.idesc, acc);
+#pragma unroll
+            for (int h = 0; h < C::N_HALVES; h++) {
+              const uint64_t bd = make_desc(sb + h * C::B_HALF_BYTES + j * b_kstep, b_lbo, b_sbo, b_lay);
+              const uint32_t td = tmem_d + (uint32_t)h * BLOCK_N;
+              if (PAIR) {
+                if (p.esize == 2) umma_f16_pair(td, ad, bd, p.idesc, acc);
+                else umma_tf32_pair(td, ad, bd, p.idesc, acc);
+              } else {
+                if (p.esize == 2) umma_f16(td, ad, bd, p.idesc, acc);
+                else umma_tf32(td, ad, bd, p.idesc, acc);
+              }
             }
           }
         }
@@ -410,7 +428,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (elect_one()) { if (PAIR) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]); }
         __syncwarp();
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> global =====
@@ -423,11 +441,11 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tfull[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = (int64_t)mb * C::TILE_M + (int64_t)rank * BLOCK_M + q * 32 + lane;
-      const int64_t col0 = (int64_t)nb * BLOCK_N;
+      const int64_t col0 = (int64_t)nb * C::TILE_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BLOCK_N;
       const int64_t crow = (int64_t)bi * p.c_bs + row * p.c_rs;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; c++) {
+      for (int c = 0; c < C::TILE_N / 32; c++) {
         uint32_t v[32];
         if (p.num_kb > 0) {
           tmem_ld32(taddr + c * 32, v);
@@ -474,7 +492,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (PAIR) mbar_arrive_cluster(leader_addr(&tempty[as]));
         else mbar_arrive(&tempty[as]);
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -551,6 +569,14 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   if (const char *f = getenv("NX_CUDA_MM_PAIR")) pair = f[0] == '1';  // test / tuning override
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   const int b_rows = pair ? BLOCK_N / 2 : BLOCK_N;
+  // 256 x 512 tiles (Cfg<true, true>): an experiment that stays opt-in (NX_CUDA_MM_WIDE=1). It moves
+  // a quarter fewer L2 bytes per flop and is bit-identical to the 256 x 256 kernel, but measured
+  // SLOWER (8192^3: 1284 vs 1395 TFLOP/s; 16384^3 equal): 4 smem stages instead of 7 and an epilogue
+  // that no longer overlaps cost more than the saved L2 traffic buys -- so the 256 x 256 kernel's
+  // 77 % tensor-pipe activity is not an L2-bandwidth limit (profiles/mm_wide_r01.json).
+  bool wide = false;
+  if (const char *f = getenv("NX_CUDA_MM_WIDE")) wide = pair && f[0] == '1' && q.n % (2 * BLOCK_N) == 0;
+  const int tile_n = wide ? 2 * BLOCK_N : BLOCK_N;
 
   TcParams p;
   p.m = q.m; p.n = q.n; p.k = q.k; p.nbatch = q.nbatch;
@@ -558,7 +584,7 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.esize = esize;
   p.block_k = ROW_BYTES / esize;
   p.num_m = (int)((q.m + tile_m - 1) / tile_m);
-  p.num_n = (int)((q.n + BLOCK_N - 1) / BLOCK_N);
+  p.num_n = (int)((q.n + tile_n - 1) / tile_n);
   p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
   p.a_batched = a_b; p.b_batched = b_b;
   p.group = 8;
@@ -600,23 +626,25 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<false>::SMEM_BYTES));
-    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true>::SMEM_BYTES));
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true, true>::SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
   if (!pair) {
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    nxc_mm_tc_kernel<false><<<grid, NUM_THREADS, Cfg<false>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
+    nxc_mm_tc_kernel<false, false><<<grid, NUM_THREADS, Cfg<false>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
   } else {
     const int64_t pairs = ctx->sm_count / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<true>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = wide ? Cfg<true, true>::SMEM_BYTES : Cfg<true>::SMEM_BYTES;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -626,7 +654,8 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     void *out = (void *)q.c;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, nxc_mm_tc_kernel<true>, map_a, map_b, out, p);
+    cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, nxc_mm_tc_kernel<true, true>, map_a, map_b, out, p)
+                         : cudaLaunchKernelEx(&cfg, nxc_mm_tc_kernel<true, false>, map_a, map_b, out, p);
     if (e != cudaSuccess) return nxc_cuda_fail(ctx, e, "cluster launch");
   }
   NXC_LAUNCH_CHECK(ctx);
