@@ -89,7 +89,7 @@ typedef struct nxc_ctx nxc_ctx;
    backend/nx_backend.mli:32-39) and Nx_buffer.create / to_host / from_host
    (reference: backend_c/nx_backend.ml:50-69). Device index comes from
    NX_CUDA_DEVICE (default: LOCAL_RANK, else 0); matmul precision from
-   NX_CUDA_MATMUL in {f32 (default, exact), tf32}. */
+   NX_CUDA_MATMUL in {f32 (default), ieee, tf32}: see nxc_set_matmul_mode. */
 NXC_API nxc_status nxc_ctx_create(nxc_ctx **out);
 /* Same, on an explicit device and an existing cudaStream_t (NULL = own stream). */
 NXC_API nxc_status nxc_ctx_create_on(int device, void *cuda_stream, nxc_ctx **out);
