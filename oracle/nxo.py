@@ -563,6 +563,30 @@ def eig(x, vectors=True):
     eps = np.finfo(np.float64).eps
     for bt in range(fa.shape[0]):
         H, Z = fa[bt].copy(), np.eye(n, dtype=np.complex128)
+        # balancing, the scaling half of the reference's `balanc` (nx_c_eig.c:25-27): D^-1 A D by exact
+        # powers of two until every row's and column's 1-norm are within a factor of two
+        bal = np.ones(n)
+        for _ in range(16):
+            changed = False
+            for i in range(n):
+                c = np.sum(np.abs(H[:, i].real) + np.abs(H[:, i].imag)) - (abs(H[i, i].real) + abs(H[i, i].imag))
+                r = np.sum(np.abs(H[i, :].real) + np.abs(H[i, :].imag)) - (abs(H[i, i].real) + abs(H[i, i].imag))
+                if not (c > 0 and r > 0 and c < 1e300 and r < 1e300):
+                    continue
+                f, s_ = 1.0, c + r
+                while c < r * 0.5:
+                    f, c = f * 2.0, c * 4.0
+                while c >= r * 2.0:
+                    f, c = f * 0.5, c * 0.25
+                if (c + r) / f < 0.95 * s_:
+                    changed = True
+                    bal[i] *= f
+                    d = H[i, i]
+                    H[i, :] /= f
+                    H[:, i] *= f
+                    H[i, i] = d
+            if not changed:
+                break
         hnorm = max(np.abs(H).sum(), 1e-300)
         hi, it, total = n - 1, 0, 0
         while hi >= 0:
@@ -605,7 +629,7 @@ def eig(x, vectors=True):
                     big = abs(X[i, k_])
                     if big > 1e150:
                         X[i:k_ + 1, k_] /= big
-            V = Z @ X
+            V = (Z @ X) * bal[:, None]
             Vv[bt] = V / np.linalg.norm(V, axis=0)
     w_hv = HostView.from_array(Wv.reshape(a.shape[:-2] + (n,)), "c64")
     if not vectors:

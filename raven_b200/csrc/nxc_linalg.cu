@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(NXC_LA_THREADS) nxc_svd_kernel(const __grid_co
 
 struct NxcEigArgs {
   Cd *h, *z, *x, *vo, *w, *vs, *rs;
-  double *rc;
+  double *rc, *bal;
   int64_t n;
   int vectors;
   int *status;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eig_kernel(const __grid_co
   __shared__ double red[NXC_LA_THREADS];
   const int64_t b = blockIdx.x, n = a.n, nn = a.n * a.n;
   la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, a.vs + b * n, a.rc + b * n,
-               a.rs + b * n, red, n, a.vectors, a.status);
+               a.rs + b * n, a.bal + b * n, red, n, a.vectors, a.status);
 }
 
 // contiguous descriptor [batch..., rows, cols] of dtype dt over `data`, batch dims taken from `like`
@@ -673,6 +673,7 @@ extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tenso
   const size_t o_h = carve(nb * nn * 16), o_z = carve(nb * nn * 16);
   const size_t o_x = carve(vectors ? nb * nn * 16 : 16), o_vo = carve(vectors ? nb * nn * 16 : 16);
   const size_t o_w = carve(nb * n * 16), o_vs = carve(nb * n * 16), o_rs = carve(nb * n * 16), o_rc = carve(nb * n * 8);
+  const size_t o_bal = carve(nb * n * 8);
   const size_t o_st = carve(sizeof(int));
   char *base = NULL;
   if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
@@ -683,7 +684,7 @@ extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tenso
   if (!s) {
     NxcEigArgs a;
     a.h = (Cd *)(base + o_h); a.z = (Cd *)(base + o_z); a.x = (Cd *)(base + o_x); a.vo = (Cd *)(base + o_vo);
-    a.w = (Cd *)(base + o_w); a.vs = (Cd *)(base + o_vs); a.rs = (Cd *)(base + o_rs); a.rc = (double *)(base + o_rc);
+    a.w = (Cd *)(base + o_w); a.vs = (Cd *)(base + o_vs); a.rs = (Cd *)(base + o_rs); a.rc = (double *)(base + o_rc); a.bal = (double *)(base + o_bal);
     a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st);
     nxc_eig_kernel<<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;

@@ -478,12 +478,49 @@ NXC_HD void la3_eigh_body(const La3Thr &t, const T *a, T *gt, T *vt, T *vo, doub
 // Per batch matrix, all complex double, contiguous:
 //   h [n][n] in: the matrix; out: the triangular Schur factor      z [n][n] accumulated unitary
 //   x [n][n] scratch (triangular eigenvectors)                       vo [n][n] out: eigenvectors (columns)
-//   w [n] out: eigenvalues     vs [n] Cd, rc [n] double, rs [n] Cd scratch;  red: nt doubles
+//   w [n] out: eigenvalues     vs [n] Cd, rc [n] double, rs [n] Cd, bal [n] double scratch;  red: nt doubles
 // status: 3 = did not converge.
-NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd *vs, double *rc, Cd *rs, double *red,
-                         int64_t n, int vectors, int *status) {
+NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd *vs, double *rc, Cd *rs, double *bal,
+                         double *red, int64_t n, int vectors, int *status) {
   const double eps = 2.220446049250313e-16;
   for (int64_t e = t.tid; e < n * n; e += t.nt) z[e] = cmk((e / n) == (e % n) ? 1.0 : 0.0, 0.0);
+  for (int64_t i = t.tid; i < n; i += t.nt) bal[i] = 1.0;
+  la3_sync();
+  // Balancing, the scaling half of the reference's `balanc` (nx_c_eig.c:25-27; EISPACK balanc / LAPACK
+  // gebal without the permutation phase): a diagonal similarity D^-1 A D by exact powers of two that
+  // brings each row's and column's 1-norm together, so the QR iteration's eps * ||A|| errors are not
+  // dominated by a few huge entries. Sequential in i by nature; the two norms are CTA-wide sums.
+  for (int pass = 0; pass < 16; pass++) {
+    bool changed = false;
+    for (int64_t i = 0; i < n; i++) {
+      double cp = 0.0, rp = 0.0;
+      for (int64_t j = t.tid; j < n; j += t.nt)
+        if (j != i) { cp += cabs1(h[j * n + i]); rp += cabs1(h[i * n + j]); }
+      double c = la3_block_sum(t, cp, red);
+      const double r = la3_block_sum(t, rp, red);
+      if (!(c > 0.0) || !(r > 0.0) || !(c < 1e300) || !(r < 1e300)) continue;  // uniform: every thread holds the same sums
+      double f = 1.0;
+      const double s = c + r;
+      double g = r * 0.5;
+      while (c < g) { f *= 2.0; c *= 4.0; }
+      g = r * 2.0;
+      while (c >= g) { f *= 0.5; c *= 0.25; }
+      if ((c + r) / f < 0.95 * s) {
+        changed = true;
+        la3_sync();  // everyone has read the old sums' inputs
+        const double gi = 1.0 / f;
+        if (t.tid == 0) bal[i] *= f;
+        for (int64_t j = t.tid; j < n; j += t.nt) {
+          if (j == i) continue;
+          h[i * n + j] = cscale(h[i * n + j], gi);
+          h[j * n + i] = cscale(h[j * n + i], f);
+        }
+        la3_sync();  // ... and the next row's sums see the scaled entries
+      }
+    }
+    la3_sync();
+    if (!changed) break;
+  }
   la3_sync();
   // Householder reduction to upper Hessenberg form: H <- Q^H H Q, Z <- Z Q  (zlarfg convention:
   // Q = I - tau v v^H with v[0] = 1, Q^H x = beta e1, beta real)
@@ -655,6 +692,8 @@ NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd
     for (int64_t j = 0; j <= k; j++) acc = cadd(acc, cmul(z[r * n + j], x[j * n + k]));
     vo[e] = acc;
   }
+  la3_sync();
+  for (int64_t e = t.tid; e < n * n; e += t.nt) vo[e] = cscale(vo[e], bal[e / n]);  // undo the balancing: v = D y
   la3_sync();
   for (int64_t k = t.tid; k < n; k += t.nt) {
     double big = 0.0;

@@ -9,7 +9,7 @@ import raven_b200.backend as B
 from raven_b200 import InvalidArgument
 from tests import harness as H
 from tests.golden.make_golden_tier3 import eig_inputs, svd_inputs
-from tests.test_oracle_tier3 import TOL, check_eig, check_svd, eig_set_err
+from tests.test_oracle_tier3 import TOL, _badly_scaled, check_eig, check_svd, eig_set_err
 
 pytestmark = pytest.mark.gpu
 
@@ -102,3 +102,14 @@ def test_tier3_errors_and_empty(ctx):
         B.svd(up(np.ones((2, 2), dtype=np.int32), "i32"))
     u, s, vh = B.svd(up(np.zeros((0, 3)), "f64"), full_matrices=True)
     assert tuple(u.shape) == (0, 0) and tuple(s.shape) == (0,) and tuple(vh.shape) == (3, 3)
+
+
+def test_eig_balances_badly_scaled_input(ctx, oracle):
+    """D^-1 A D with entries spread over 24 decades: the eigenvalues of A to 1e-12, as the reference
+    (which balances, nx_c_eig.c:25-27) returns them"""
+    a, bad = _badly_scaled(20, 2)
+    hv = H.HostView.from_array(bad, "f64")
+    w = H.download(B.eigvals(H.upload(ctx, hv)))
+    want = np.linalg.eigvals(a)
+    assert eig_set_err(w, want) <= 1e-12 * np.abs(want).max()
+    assert eig_set_err(oracle.eig(hv, False).numpy(), want) <= 1e-12 * np.abs(want).max()

@@ -180,3 +180,22 @@ def test_eig_kernel_body_defective_matrix_stays_finite(emu):
     w, v = emu_eig(emu, a)
     assert np.abs(w - 1).max() <= 1e-12 and np.isfinite(v).all()
     assert np.abs(a @ v - v * w[None, :]).max() <= 1e-10
+
+
+def _badly_scaled(n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, n))
+    d = 10.0 ** rng.integers(-6, 7, n)
+    return a, (a * d[None, :]) / d[:, None]   # D^-1 A D: the same spectrum, entries spread over 24 decades
+
+
+def test_eig_kernel_body_balances_badly_scaled_input(emu):
+    """the scaling half of the reference's `balanc` (nx_c_eig.c:25-27): without it the QR iteration's
+    eps * ||A|| errors swamp the small eigenvalues of D^-1 A D"""
+    for n, seed in ((8, 1), (20, 2), (50, 3)):
+        a, bad = _badly_scaled(n, seed)
+        want = np.linalg.eigvals(a)
+        w, v = emu_eig(emu, bad)
+        assert eig_set_err(w, want) <= 1e-12 * np.abs(want).max(), n
+        assert np.abs(bad @ v - v * w[None, :]).max() <= 1e-10 * np.abs(bad).max()
+        assert np.abs(np.linalg.norm(v, axis=0) - 1).max() <= 1e-12
