@@ -540,14 +540,21 @@ struct NxcEigArgs {
   double *rc, *bal;
   int64_t n;
   int vectors;
+  int smem_rows;
   int *status;
 };
 
 __global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eig_kernel(const __grid_constant__ NxcEigArgs a) {
   __shared__ double red[NXC_LA_THREADS];
+  extern __shared__ __align__(16) unsigned char eig_smem[];
   const int64_t b = blockIdx.x, n = a.n, nn = a.n * a.n;
-  la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, a.vs + b * n, a.rc + b * n,
-               a.rs + b * n, a.bal + b * n, red, n, a.vectors, a.status);
+  // the Householder vector and the rotation chain are read by every thread at every step: keep them in
+  // shared memory when they fit (40 bytes per row), in global scratch otherwise
+  Cd *vs = a.smem_rows ? (Cd *)eig_smem : a.vs + b * n;
+  Cd *rs = a.smem_rows ? vs + n : a.rs + b * n;
+  double *rc = a.smem_rows ? (double *)(rs + n) : a.rc + b * n;
+  la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, vs, rc, rs,
+               a.bal + b * n, red, n, a.vectors, a.status);
 }
 
 // contiguous descriptor [batch..., rows, cols] of dtype dt over `data`, batch dims taken from `like`
@@ -686,7 +693,11 @@ extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tenso
     a.h = (Cd *)(base + o_h); a.z = (Cd *)(base + o_z); a.x = (Cd *)(base + o_x); a.vo = (Cd *)(base + o_vo);
     a.w = (Cd *)(base + o_w); a.vs = (Cd *)(base + o_vs); a.rs = (Cd *)(base + o_rs); a.rc = (double *)(base + o_rc); a.bal = (double *)(base + o_bal);
     a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st);
-    nxc_eig_kernel<<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a);
+    size_t smem = (size_t)n * 40;
+    a.smem_rows = smem <= 160 * 1024;
+    if (!a.smem_rows) smem = 0;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(nxc_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nxc_eig_kernel<<<(unsigned)nbatch, NXC_LA_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "eig");
   }
