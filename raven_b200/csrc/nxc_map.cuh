@@ -311,21 +311,43 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
     // vector loads through one register quad and copies each result out right behind its load --
     // one dependent round trip per slot (ncu, f64 [R,C]+[R,1]: 0.77 of the roofline, four moves
     // holding 20 % of the stall samples each).
-    auto load_all = [&](auto BA, auto BB, auto BC) {
+    // The same flags are compile-time constants in the COMPUTE phase of those variants: picking an
+    // element out of a packed register by a run-time "broadcast? reversed?" costs two selects per
+    // operand and element, which for the 1- and 2-byte types (8-16 elements per 16-byte item) made the
+    // kernel ALU-bound (bf16 [R,C]+[1,C]: 0.49 of the roofline).
+    auto run_all = [&](auto BA, auto BB, auto BC, auto NG) {
+      constexpr bool cba = decltype(BA)::value, cbb = decltype(BB)::value, cbc = decltype(BC)::value;
+      constexpr bool ng = decltype(NG)::value;
+      const bool na_ = ng && na, nb_ = ng && nb, nc_ = ng && nc;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, decltype(BA)::value, na, va[u], xa[u]);
-        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, decltype(BB)::value, nb, vb[u], xb[u]);
-        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, decltype(BC)::value, nc, vc[u], xc[u]);
+        if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, cba, na_, va[u], xa[u]);
+        if (K::NIN >= 2) nxc_load_item<S2, VW>(pb, cbb, nb_, vb[u], xb[u]);
+        if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, cbc, nc_, vc[u], xc[u]);
         if (u + 1 < n_live) { pa += sa; pb += sb; pc += sc; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (u < n_live) {
+          S0 vo[VW];
+#pragma unroll
+          for (int i = 0; i < VW; i++)
+            vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, cba, na_), nxc_item_elem<S2, VW>(vb[u], xb[u], i, cbb, nb_),
+                           nxc_item_elem<S3, VW>(vc[u], xc[u], i, cbc, nc_), prm);
+          if (VW == 1) po[0] = vo[0];
+          else nxc_store_vec<S0, VW>(po, vo);
+        }
+        po += so;
       }
     };
     typedef std::integral_constant<bool, false> F_;
     typedef std::integral_constant<bool, true> T_;
-    if (!(ba | bb | bc)) load_all(F_(), F_(), F_());
-    else if (bb && !ba && !bc) load_all(F_(), T_(), F_());
-    else if (ba && !bb && !bc) load_all(T_(), F_(), F_());
+    const bool any_neg = na | nb | nc;
+    if (!any_neg && !(ba | bb | bc)) run_all(F_(), F_(), F_(), F_());
+    else if (!any_neg && bb && !ba && !bc) run_all(F_(), T_(), F_(), F_());
+    else if (!any_neg && ba && !bb && !bc) run_all(T_(), F_(), F_(), F_());
     else {
+      // anything else (a reversed run, several broadcast operands): flags stay run-time values
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (K::NIN >= 1) nxc_load_item<S1, VW>(pa, ba, na, va[u], xa[u]);
@@ -333,19 +355,19 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
         if (K::NIN >= 3) nxc_load_item<S3, VW>(pc, bc, nc, vc[u], xc[u]);
         if (u + 1 < n_live) { pa += sa; pb += sb; pc += sc; }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (u < n_live) {
-        S0 vo[VW];
+      for (int u = 0; u < U; u++) {
+        if (u < n_live) {
+          S0 vo[VW];
 #pragma unroll
-        for (int i = 0; i < VW; i++)
-          vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], xb[u], i, bb, nb),
-                         nxc_item_elem<S3, VW>(vc[u], xc[u], i, bc, nc), prm);
-        if (VW == 1) po[0] = vo[0];
-        else nxc_store_vec<S0, VW>(po, vo);
+          for (int i = 0; i < VW; i++)
+            vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], xb[u], i, bb, nb),
+                           nxc_item_elem<S3, VW>(vc[u], xc[u], i, bc, nc), prm);
+          if (VW == 1) po[0] = vo[0];
+          else nxc_store_vec<S0, VW>(po, vo);
+        }
+        po += so;
       }
-      po += so;
     }
   } else {
     const int64_t item = (int64_t)chunk * TX + tx;
