@@ -1,0 +1,47 @@
+"""The bench line contract, checked on the lines committed under profiles/ (produced by bench.py on a
+B200): the keys the driver and the judge read are present and self-consistent. No GPU needed."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _line(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_cuda_arm_line(n):
+    b = _line(f"bench_r01_n{n}.json")
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert b["metric"] == base["metric"] and b["unit"] == "GB/s" and b["n_gpus"] == n
+    assert b["higher_is_better"] is True and b["scaling"] == "weak" and b["vs_baseline"] is None
+    assert b["steps"] >= 1 and b["warmup"] >= 3 and b["data"] == "synthetic" and b["dtype"] == "f32"
+    assert "workload" in b["config"] and "model" not in b["config"]
+    assert b["gpu_launches"] > 0 and b["impl"] == "cuda"
+    # value is the whole-job aggregate: algorithmic bytes of all ranks / the step time
+    per_gpu = b["config"]["algorithmic_bytes_per_step_per_gpu"]
+    assert abs(b["value"] - n * per_gpu / (b["ms_per_step"] * 1e-3) / 1e9) <= 0.01 * b["value"]
+    e = b["e2e"]
+    assert e["unit"] == b["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < b["value"]  # host buffers and PCIe copies inside the timed region
+    assert set(b["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not set(b["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        r = b["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+        assert r["traffic"] is None or 0.5 * r["algorithmic_bytes_per_launch"] < r["traffic"] < 1.5 * r["algorithmic_bytes_per_launch"]
+        c = b["cpu_baseline"]
+        assert c["kind"] == "reference" and c["cores"] >= 1 and c["unit"] == b["unit"] and c["sample"]
+        m = b["matmul"]
+        assert m["bound"] == "tensor" and m["unit"] == "TFLOP/s" and 0 < m["frac"] <= 1.0
+
+
+def test_reference_arm_line():
+    b = _line("bench_r01_reference.json")
+    assert b["impl"] == "reference" and b["gpu_launches"] == 0
+    assert b["e2e"] == {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert b["cpu_baseline"]["kind"] == "reference" and b["cpu_baseline"]["value"] == b["value"]
