@@ -129,6 +129,32 @@ NXC_API nxc_status nxc_memset(nxc_ctx *ctx, void *dst_dev, int byte, size_t byte
    at once: the engine defers the release until the copy has finished. */
 NXC_API nxc_status nxc_d2h_async(nxc_ctx *ctx, void *dst_host_pinned, const void *src_dev, size_t bytes);
 
+/* ---- step capture (new; no reference counterpart -- the reference's eager backend pays one
+   function call per op, a device backend pays one LAUNCH per op, and a training step is a few
+   thousand of them). Between nxc_capture_begin and nxc_capture_end every call on the context is
+   recorded into a CUDA graph instead of running; nxc_graph_launch replays the whole step with one
+   launch, any number of times, on the context's stream.
+     - memory: while capturing, nxc_alloc / nxc_free are served by an arena the graph owns, so
+       the handles created during the capture keep their addresses and are the replay's outputs;
+       they stay valid until nxc_graph_destroy, and nxc_free of them afterwards is a no-op.
+       Buffers that existed before the capture (inputs, parameters) are read in place by every
+       replay: keep them alive and update them in place (nxc_copy into them) between replays.
+     - calls that block or read back (nxc_sync, nxc_d2h, the checked gather / scatter range test,
+       the linalg status words) return "operation not allowed while a step is being captured";
+       nxc_gather / nxc_scatter defer their range check to the next nxc_sync as with
+       NX_CUDA_SYNC_CHECKS=0. nxc_h2d / nxc_d2h_async are recorded as copy nodes and need
+       page-locked host memory (a replay re-reads / re-writes the same host buffer).
+     - collectives are capturable (the peer-memory exchanges keep their epoch on the device);
+       every rank must replay the same graphs in the same order.
+   nxc_graph_kernels = kernel nodes in the graph (what one replay adds to nxc_launch_count). */
+typedef struct nxc_graph nxc_graph;
+NXC_API nxc_status nxc_capture_begin(nxc_ctx *ctx);
+NXC_API nxc_status nxc_capture_end(nxc_ctx *ctx, nxc_graph **out);
+NXC_API nxc_status nxc_graph_launch(nxc_ctx *ctx, nxc_graph *g);
+NXC_API uint64_t nxc_graph_kernels(nxc_graph *g);
+NXC_API size_t nxc_graph_arena_bytes(nxc_graph *g);
+NXC_API void nxc_graph_destroy(nxc_ctx *ctx, nxc_graph *g);
+
 /* ---- map family -----------------------------------------------------------
    replaces caml_nx_c_{neg..erf}, caml_nx_c_{add..shr}, caml_nx_c_cmp*,
    caml_nx_c_where, caml_nx_c_cast, caml_nx_c_copy (reference:
@@ -238,7 +264,8 @@ NXC_API nxc_status nxc_gather(nxc_ctx *ctx, const nxc_tensor *out, const nxc_ten
                       const nxc_tensor *indices_i32, int axis);
 /* nxc_gather for indices the backend produced itself (argmax / argmin / argsort results): the
    range flag is not read back, so the call does not drain the stream. Out-of-range indices
-   are still never dereferenced. */
+   are still never dereferenced, and the flag is sticky: the next nxc_sync / nxc_d2h raises
+   "index out of bounds for the gathered/scattered axis". */
 NXC_API nxc_status nxc_gather_trusted(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *data,
                                       const nxc_tensor *indices_i32, int axis);
 /* `out` is pre-seeded with the template; mode 0 = Set (last write wins), 1 = Add. */
@@ -270,12 +297,28 @@ NXC_API nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const void *
 NXC_API nxc_status nxc_dist_finalize(nxc_ctx *ctx);
 /* 1 when nxc_dist_init mapped every peer's mailbox (CUDA IPC over NVLink): nxc_allreduce /
    nxc_allgather of payloads up to 256 KiB per rank then run as ONE kernel that stores into the
-   peers' memory and waits on flags (allreduce folds the gathered partials in rank order with
-   the backend's own reduce, so every rank holds bit-identical results); larger payloads, the
-   async entry point and NX_CUDA_P2P=0 use NCCL. */
+   peers' memory and waits on flags (nxc_allreduce and nxc_argreduce_exchange fold what they
+   receive in the same kernel); larger payloads, the async entry point and NX_CUDA_P2P=0 use NCCL. */
 NXC_API int nxc_dist_p2p_enabled(nxc_ctx *ctx);
-/* In-place allreduce over `count` elements of `dtype`; op is an nxc_reduce_op. */
+/* In-place allreduce over `count` elements of `dtype`; op is an nxc_reduce_op. Every dtype / op the
+   single-device nxc_reduce takes. Up to 256 KiB with the mailboxes mapped: ONE kernel pushes the
+   partial to every peer, waits for theirs and folds them in rank order (bit-identical on all
+   ranks, float max / min NaN-sticky). Larger: NCCL where it has the reduction, else all-gather +
+   the backend's own reduce over the rank axis. A peer that never shows up is reported by the
+   next nxc_sync / nxc_d2h as "NCCL error" (detail: the exchange timed out) -- never a hang, never
+   silently undefined data. */
 NXC_API nxc_status nxc_allreduce(nxc_ctx *ctx, void *dev_buf, int64_t count, int dtype, int op);
+/* The finish of an argmax / argmin along an axis whose slabs live on the ranks, in ONE kernel over
+   the mailboxes: `local_idx_i32` is this rank's nxc_argreduce result over its slab `x_local`
+   along `axis` (squeezed, C-contiguous), `idx_offset` the global position of the slab's first
+   element along that axis; `out_i32` (same shape, C-contiguous) receives the GLOBAL index of the
+   extreme over all ranks by the single-device rule (first index on ties, first NaN wins;
+   reference: nx_c_fold.c:93-101). At most nxc_argreduce_exchange_max_outputs outputs (0 when the
+   mailboxes are not mapped: use all-gathers then). */
+NXC_API nxc_status nxc_argreduce_exchange(nxc_ctx *ctx, int is_max, const nxc_tensor *out_i32,
+                                          const nxc_tensor *x_local, const nxc_tensor *local_idx_i32, int axis,
+                                          int64_t idx_offset);
+NXC_API int64_t nxc_argreduce_exchange_max_outputs(nxc_ctx *ctx);
 NXC_API nxc_status nxc_allgather(nxc_ctx *ctx, const void *dev_send, void *dev_recv,
                          int64_t bytes_per_rank);
 /* The same allreduce on the context's communication stream: ordered after the work already

@@ -5,7 +5,10 @@
  * reads: packages/nx/lib/backend_c/nx_c.h:47-61, 420-434), calls one nxc_* entry
  * point (an asynchronous launch on the context stream) and maps a non-NULL status to
  * Invalid_argument / Failure "<op>: <status>" exactly as the reference's funnel does
- * (nx_c_engine.c:42-52, 1345-1351). UNVERIFIED: never compiled here (no OCaml).
+ * (nx_c_engine.c:42-52, 1345-1351). There is no OCaml toolchain in the build image; this file is
+ * nevertheless EXECUTED by the GPU suite: tests/test_gpu_ocaml_stubs.py compiles it against the
+ * OCaml C API declarations plus a small runtime shim (custom-block allocation, the two raisers) and
+ * drives every stub with fabricated OCaml values, as oracle/ref.py does for the reference's stubs.
  */
 #include <stdio.h>
 #include <string.h>
@@ -82,11 +85,15 @@ CAMLprim value nx_cuda_alloc(value vctx, value vbytes) {
 CAMLprim value nx_cuda_of_host(value vctx, value vbuf) {
   CAMLparam2(vctx, vbuf);
   CAMLlocal1(v);
-  struct caml_ba_array *ba = Caml_ba_array_val(vbuf);
-  size_t n = caml_ba_byte_size(ba);
+  size_t n = caml_ba_byte_size(Caml_ba_array_val(vbuf));
   v = nx_cuda_alloc(vctx, Val_long(n ? n : 16));
+  /* nx_cuda_alloc allocates a custom block, so the GC may have run and moved vbuf's block (it is
+     rooted: the VALUE was updated). Everything derived from it is fetched only now. The bigarray's
+     data lives outside the OCaml heap and does not move across the blocking section. */
+  struct caml_ba_array *ba = Caml_ba_array_val(vbuf);
+  void *src = ba->data;
   nxc_ctx *ctx = Ctx_val(vctx);
-  nxc_status s = nxc_h2d(ctx, Devbuf_val(v)->ptr, ba->data, n);
+  nxc_status s = nxc_h2d(ctx, Devbuf_val(v)->ptr, src, n);
   if (!s) { caml_enter_blocking_section(); s = nxc_sync(ctx); caml_leave_blocking_section(); }
   if (s) raise_status("from_host", ctx, s);
   CAMLreturn(v);
@@ -104,6 +111,9 @@ CAMLprim value nx_cuda_to_host(value vctx, value vdev, value vbuf) {
   CAMLreturn(Val_unit);
 }
 
+/* op name for the exception text; an out-of-range code (the engine answers "unknown operation
+   code") must not index past the table */
+#define OP_NAME(table, i) (((i) >= 0 && (size_t)(i) < sizeof(table) / sizeof((table)[0])) ? (table)[i] : "op")
 static const char *UN[] = {"neg","recip","abs","sign","sqrt","exp","log","sin","cos","tan","asin","acos","atan",
                            "sinh","cosh","tanh","trunc","ceil","floor","round","erf"};
 static const char *BIN[] = {"add","sub","mul","idiv","fdiv","mod","max","min","pow","atan2","xor","or","and","shl","shr"};
@@ -115,21 +125,21 @@ CAMLprim value nx_cuda_map1(value vop, value vout, value va) {
   CAMLparam3(vop, vout, va);
   nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(va, &a);
   nxc_status s = nxc_map1(CTX_OF(vout), Int_val(vop), &o, &a);
-  if (s) raise_status(UN[Int_val(vop)], CTX_OF(vout), s);
+  if (s) raise_status(OP_NAME(UN, Int_val(vop)), CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
 CAMLprim value nx_cuda_map2(value vop, value vout, value va, value vb) {
   CAMLparam4(vop, vout, va, vb);
   nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
   nxc_status s = nxc_map2(CTX_OF(vout), Int_val(vop), &o, &a, &b);
-  if (s) raise_status(BIN[Int_val(vop)], CTX_OF(vout), s);
+  if (s) raise_status(OP_NAME(BIN, Int_val(vop)), CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
 CAMLprim value nx_cuda_cmp(value vop, value vout, value va, value vb) {
   CAMLparam4(vop, vout, va, vb);
   nxc_tensor o, a, b; tensor_of_value(vout, &o); tensor_of_value(va, &a); tensor_of_value(vb, &b);
   nxc_status s = nxc_cmp(CTX_OF(vout), Int_val(vop), &o, &a, &b);
-  if (s) raise_status(CMP[Int_val(vop)], CTX_OF(vout), s);
+  if (s) raise_status(OP_NAME(CMP, Int_val(vop)), CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
 CAMLprim value nx_cuda_where(value vout, value vc, value va, value vb) {
@@ -165,7 +175,7 @@ CAMLprim value nx_cuda_reduce(value vop, value vout, value vin, value vaxes) {
   if (n > NXC_MAX_NDIM) caml_failwith("ndim exceeds NX_C_MAX_NDIM");
   for (int i = 0; i < n; i++) axes[i] = Int_val(Field(vaxes, i));
   nxc_status s = nxc_reduce(CTX_OF(vout), Int_val(vop), &o, &a, axes, n);
-  if (s) raise_status(RED[Int_val(vop)], CTX_OF(vout), s);
+  if (s) raise_status(OP_NAME(RED, Int_val(vop)), CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
 CAMLprim value nx_cuda_argreduce(value vmax, value vout, value vin, value vaxis) {
@@ -179,7 +189,7 @@ CAMLprim value nx_cuda_scan(value vop, value vout, value vin, value vaxis) {
   CAMLparam4(vop, vout, vin, vaxis);
   nxc_tensor o, a; tensor_of_value(vout, &o); tensor_of_value(vin, &a);
   nxc_status s = nxc_scan(CTX_OF(vout), Int_val(vop), &o, &a, Int_val(vaxis));
-  if (s) raise_status(SCAN[Int_val(vop)], CTX_OF(vout), s);
+  if (s) raise_status(OP_NAME(SCAN, Int_val(vop)), CTX_OF(vout), s);
   CAMLreturn(Val_unit);
 }
 CAMLprim value nx_cuda_matmul(value vout, value va, value vb) {

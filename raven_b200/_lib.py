@@ -96,6 +96,14 @@ SYMBOLS = {
     "nxc_allreduce_async": (_S, [_P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "nxc_comm_wait": (_S, [_P]),
     "nxc_allgather": (_S, [_P, _P, _P, ctypes.c_int64]),
+    "nxc_argreduce_exchange": (_S, [_P, ctypes.c_int, _T, _T, _T, ctypes.c_int, ctypes.c_int64]),
+    "nxc_argreduce_exchange_max_outputs": (ctypes.c_int64, [_P]),
+    "nxc_capture_begin": (_S, [_P]),
+    "nxc_capture_end": (_S, [_P, ctypes.POINTER(_P)]),
+    "nxc_graph_launch": (_S, [_P, _P]),
+    "nxc_graph_kernels": (ctypes.c_uint64, [_P]),
+    "nxc_graph_arena_bytes": (ctypes.c_size_t, [_P]),
+    "nxc_graph_destroy": (None, [_P, _P]),
 }
 
 _lib = None
@@ -127,7 +135,7 @@ def check(ctx_ptr, op: str, status):
     lib = load()
     msg = status.decode()
     detail = ""
-    if msg in ("CUDA error", "NCCL error") or msg.startswith("no CUDA device"):
+    if msg in ("CUDA error", "NCCL error") or msg.startswith(("no CUDA device", "operation not allowed while")):
         d = lib.nxc_last_error(ctx_ptr)
         detail = f" [{d.decode()}]" if d else ""
     text = f"{op}: {msg}{detail}"

@@ -52,6 +52,7 @@ class Context:
         self._p = p
         self._lib = lib
         self._pinned = []   # [lo, hi) address ranges handed out by pinned_empty
+        self._capturing = None   # the Capture being recorded, if any
 
     @property
     def ptr(self):
@@ -96,10 +97,63 @@ class Context:
         if self._lib.nxc_set_matmul_mode(self._p, mode.encode()) != 0:
             raise InvalidArgument(f"set_matmul_mode: unknown mode {mode!r}")
 
+    def capture(self) -> "Capture":
+        """`with ctx.capture() as g: outs = step()` records the ops issued inside the block into a
+        CUDA graph instead of running them (nxc_capture_begin / nxc_capture_end); `g.launch()` then
+        replays the whole step with one launch. Tensors created inside the block are the replay's
+        outputs: they keep their addresses, are rewritten by every `g.launch()`, and stay valid as
+        long as `g` does (each holds a reference to it). Tensors that existed before the block are
+        read in place by every replay -- keep them alive, refresh them with `assign`."""
+        return Capture(self)
+
     def close(self):
         if self._p:
             self._lib.nxc_ctx_destroy(self._p)
             self._p = None
+
+
+class Capture:
+    """A captured step (see Context.capture)."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        self._g = None
+        self.kernels = 0
+        self.arena_bytes = 0
+
+    def __enter__(self):
+        check(self.ctx.ptr, "capture_begin", self.ctx._lib.nxc_capture_begin(self.ctx.ptr))
+        self.ctx._capturing = self
+        return self
+
+    def __exit__(self, et, ev, tb):
+        self.ctx._capturing = None
+        g = ctypes.c_void_p()
+        st = self.ctx._lib.nxc_capture_end(self.ctx.ptr, ctypes.byref(g))
+        if et is None:
+            check(self.ctx.ptr, "capture_end", st)
+            self._g = g
+            self.kernels = int(self.ctx._lib.nxc_graph_kernels(g))
+            self.arena_bytes = int(self.ctx._lib.nxc_graph_arena_bytes(g))
+        elif not st and g:
+            self.ctx._lib.nxc_graph_destroy(self.ctx.ptr, g)
+        return False
+
+    def launch(self):
+        if self._g is None:
+            raise Failure("graph_launch: nothing was captured")
+        check(self.ctx.ptr, "graph_launch", self.ctx._lib.nxc_graph_launch(self.ctx.ptr, self._g))
+
+    def close(self):
+        if self._g is not None and self.ctx._p:
+            self.ctx._lib.nxc_graph_destroy(self.ctx.ptr, self._g)
+        self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def create_context(device=None, stream=None) -> Context:
@@ -109,11 +163,12 @@ def create_context(device=None, stream=None) -> Context:
 class _Buffer:
     """A device allocation, shared by every handle viewing it."""
 
-    __slots__ = ("ctx", "ptr", "nbytes", "owned", "_host_src", "__weakref__")
+    __slots__ = ("ctx", "ptr", "nbytes", "owned", "_host_src", "_graph", "__weakref__")
 
     def __init__(self, ctx: Context, nbytes: int, ptr=None):
         self.ctx = ctx
         self.nbytes = int(nbytes)
+        self._graph = ctx._capturing   # arena memory lives as long as the captured graph does
         if ptr is None:
             p = ctypes.c_void_p()
             check(ctx.ptr, "buffer", ctx._lib.nxc_alloc(ctx.ptr, self.nbytes, ctypes.byref(p)))
@@ -125,7 +180,9 @@ class _Buffer:
 
     def __del__(self):
         try:
-            if self.owned and self.ptr and self.ctx._p:
+            # arena memory is recycled only while its capture is still recording; afterwards the
+            # graph owns it (the engine would ignore the call) or has already released it
+            if self.owned and self.ptr and self.ctx._p and (self._graph is None or self.ctx._capturing is self._graph):
                 self.ctx._lib.nxc_free(self.ctx.ptr, self.ptr)
         except Exception:
             pass

@@ -9,7 +9,7 @@
 // dependency. Only the handful of symbols used are declared here.
 #include <dlfcn.h>
 
-#include "nxc_common.cuh"
+#include "nxc_dist.cuh"
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -74,6 +74,7 @@ extern "C" nxc_status nxc_dist_unique_id(void *id_out) {
 }
 
 extern "C" nxc_status nxc_dist_init(nxc_ctx *ctx, int rank, int world, const void *id_128) {
+  NXC_TRACE(ctx, "nxc_dist_init");
   nxc_status s = nccl_load(ctx);
   if (s) return s;
   NXC_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -102,100 +103,33 @@ extern "C" nxc_status nxc_dist_finalize(nxc_ctx *ctx) {
 
 // ---- small exchanges over peer memory ----------------------------------------------------
 // The exchange step of a sharded reduction moves a few bytes to a few KB per rank; through
-// NCCL that is one ~10-20 us kernel per call and the sharded step is made of five of them.
-// Here every rank owns a MAILBOX (plain cudaMalloc, exported with CUDA IPC and mapped by every
-// peer at nxc_dist_init), and one kernel does the whole all-gather: CTA (s, c) stores chunk c
-// of this rank's payload straight into peer s's mailbox over NVLink, releases a flag there,
-// then waits for chunk c from rank s in its OWN mailbox and copies it to the output. Slots and
-// flags are double-buffered on the parity of a per-context epoch: a slot is rewritten at epoch
-// e+2, which a sender can only reach after it saw this rank's epoch e+1 flags, i.e. after this
-// rank finished reading epoch e. allreduce = this all-gather + the backend's own reduce over
-// the rank axis, in rank order on every rank, so all ranks hold bit-identical results (NCCL
-// promises that only per algorithm choice). Payloads above the slot size, async (comm-stream)
-// collectives and NX_CUDA_P2P=0 use NCCL.
-#define NXC_P2P_MAX_WORLD 16
-#define NXC_P2P_SLOT_BYTES ((size_t)256 << 10)
-#define NXC_P2P_CHUNK_BYTES ((size_t)16 << 10)
-#define NXC_P2P_MAX_CHUNKS (NXC_P2P_SLOT_BYTES / NXC_P2P_CHUNK_BYTES)
-
-struct nxc_p2p {
-  int world, rank;
-  char *local;                      // this rank's mailbox
-  char *peer[NXC_P2P_MAX_WORLD];    // every rank's mailbox as mapped here (peer[rank] == local)
-  uint32_t epoch;
-  int *status;                      // device word: nonzero after a wait timed out
-};
-struct NxcP2PArgs {
-  char *peer[NXC_P2P_MAX_WORLD];
-  int world, rank;
-  uint32_t epoch;
-  int chunks;
-  int64_t bytes;                    // payload per rank
-  const char *send;
-  char *recv;                       // [world][bytes]
-  int *status;
-};
-static __host__ __device__ inline size_t nxc_p2p_data_bytes(int world) { return 2 * (size_t)world * NXC_P2P_SLOT_BYTES; }
-static inline size_t nxc_p2p_total_bytes(int world) {
-  return nxc_p2p_data_bytes(world) + 2 * (size_t)world * NXC_P2P_MAX_CHUNKS * sizeof(uint32_t);
-}
-
-__device__ __forceinline__ void nxc_st_release_sys(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t nxc_ld_acquire_sys(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint64_t nxc_globaltimer() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-__global__ void __launch_bounds__(256) nxc_p2p_allgather_kernel(const NxcP2PArgs a) {
-  const int s = blockIdx.x / a.chunks, c = blockIdx.x - s * a.chunks;
-  const int par = a.epoch & 1;
+// NCCL that is one ~10-20 us kernel per call. Here ONE kernel does the whole all-gather over
+// the mailboxes of nxc_dist.cuh: CTA (s, c) stores chunk c of this rank's payload straight into
+// peer s's mailbox over NVLink, releases a flag there, then waits for chunk c from rank s in its
+// OWN mailbox and copies it to the output. nxc_allreduce and the arg-reduce finish go one step
+// further (nxc_dist_fold.cu): the same kernel that receives the partials folds them, in rank
+// order on every rank, so all ranks hold bit-identical results (NCCL promises that only per
+// algorithm choice). Payloads above the slot size, async (comm-stream) collectives and
+// NX_CUDA_P2P=0 use NCCL.
+__global__ void __launch_bounds__(256) nxc_p2p_allgather_kernel(const NxcP2P a, int chunks, int64_t bytes,
+                                                                const char *__restrict__ send, char *__restrict__ recv) {
+  const int s = blockIdx.x / chunks, c = blockIdx.x - s * chunks;
+  const uint32_t e = nxc_p2p_epoch(a);
   const int64_t lo = (int64_t)c * (int64_t)NXC_P2P_CHUNK_BYTES;
-  int64_t len = a.bytes - lo;
+  int64_t len = bytes - lo;
   if (len > (int64_t)NXC_P2P_CHUNK_BYTES) len = NXC_P2P_CHUNK_BYTES;
-  const size_t flags_off = nxc_p2p_data_bytes(a.world);
-  // push: my chunk c -> peer s, slot [par][my rank]
-  {
-    char *dst = a.peer[s] + ((size_t)(par * a.world + a.rank)) * NXC_P2P_SLOT_BYTES + lo;
-    const char *src = a.send + lo;
-    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-      const int64_t nv = len >> 4;
-      for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
-      for (int64_t i = (nv << 4) + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
-    } else {
-      for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t *flag = (uint32_t *)(a.peer[s] + flags_off) + ((size_t)(par * a.world + a.rank)) * NXC_P2P_MAX_CHUNKS + c;
-      nxc_st_release_sys(flag, a.epoch);
-    }
-  }
+  // push: my chunk c -> peer s
+  nxc_p2p_copy_out(nxc_p2p_slot(a, s, e, a.rank) + lo, send + lo, len);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) nxc_st_release_sys(nxc_p2p_flag(a, s, e, a.rank, c), e);
   // pull: chunk c of rank s has to land in my mailbox
   __shared__ int ok;
-  if (threadIdx.x == 0) {
-    const uint32_t *flag = (const uint32_t *)(a.peer[a.rank] + flags_off) + ((size_t)(par * a.world + s)) * NXC_P2P_MAX_CHUNKS + c;
-    const uint64_t t0 = nxc_globaltimer();
-    int good = 1;
-    while (nxc_ld_acquire_sys(flag) != a.epoch) {
-      __nanosleep(64);
-      if (nxc_globaltimer() - t0 > 20000000000ull) { good = 0; atomicExch(a.status, 1); break; }  // 20 s: a peer died
-    }
-    ok = good;
-  }
+  if (threadIdx.x == 0) ok = nxc_p2p_wait(nxc_p2p_flag(a, a.rank, e, s, c), e, a.status) ? 1 : 0;
   __syncthreads();
-  if (!ok) return;
-  {
-    const char *src = a.peer[a.rank] + ((size_t)(par * a.world + s)) * NXC_P2P_SLOT_BYTES + lo;
-    char *dst = a.recv + (int64_t)s * a.bytes + lo;
+  if (ok) {
+    const char *src = nxc_p2p_slot(a, a.rank, e, s) + lo;
+    char *dst = recv + (int64_t)s * bytes + lo;
     if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
       const int64_t nv = len >> 4;
       for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) ((uint4 *)dst)[i] = __ldcv((const uint4 *)src + i);
@@ -204,6 +138,7 @@ __global__ void __launch_bounds__(256) nxc_p2p_allgather_kernel(const NxcP2PArgs
       for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcv(src + i);
     }
   }
+  nxc_p2p_finish(a, e);
 }
 
 static void nxc_p2p_teardown(nxc_ctx *ctx) {
@@ -212,7 +147,7 @@ static void nxc_p2p_teardown(nxc_ctx *ctx) {
   for (int r = 0; r < q->world; r++)
     if (r != q->rank && q->peer[r]) cudaIpcCloseMemHandle(q->peer[r]);
   if (q->local) cudaFree(q->local);
-  if (q->status) cudaFree(q->status);
+  if (q->state) cudaFree(q->state);
   free(q);
   ctx->p2p = NULL;
   cudaGetLastError();
@@ -235,7 +170,7 @@ static void nxc_p2p_setup(nxc_ctx *ctx) {
     q->world = ctx->world; q->rank = ctx->rank;
     good = cudaMalloc(&q->local, nxc_p2p_total_bytes(ctx->world)) == cudaSuccess &&
            cudaMemset(q->local, 0, nxc_p2p_total_bytes(ctx->world)) == cudaSuccess &&
-           cudaMalloc(&q->status, sizeof(int)) == cudaSuccess && cudaMemset(q->status, 0, sizeof(int)) == cudaSuccess &&
+           cudaMalloc(&q->state, 4 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(q->state, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine.h, q->local) == cudaSuccess;
   }
   mine.ok = good;
@@ -274,20 +209,21 @@ static void nxc_p2p_setup(nxc_ctx *ctx) {
 
 extern "C" int nxc_dist_p2p_enabled(nxc_ctx *ctx) { return ctx->p2p != NULL; }
 
+static nxc_status dist_usable(nxc_ctx *ctx) {
+  if (!ctx->nccl_comm) { snprintf(ctx->err, sizeof ctx->err, "%s: nxc_dist_init not called", NXC_ERR_NCCL); return NXC_ERR_NCCL; }
+  if (ctx->dist_poisoned || (ctx->hstatus && ctx->hstatus[NXC_ST_EXCHANGE])) {
+    ctx->dist_poisoned = 1;
+    snprintf(ctx->err, sizeof ctx->err, "%s: %s earlier on this communicator", NXC_ERR_NCCL, NXC_ERR_EXCHANGE_TIMEOUT);
+    return NXC_ERR_NCCL;
+  }
+  return NXC_OK;
+}
+
 static nxc_status nxc_p2p_allgather(nxc_ctx *ctx, const void *send, void *recv, int64_t bytes) {
-  nxc_p2p *q = ctx->p2p;
-  NxcP2PArgs a;
-  for (int r = 0; r < q->world; r++) a.peer[r] = q->peer[r];
-  a.world = q->world; a.rank = q->rank;
-  a.epoch = ++q->epoch;
-  if (a.epoch == 0) a.epoch = ++q->epoch;  // 0 is the cleared-flag value
-  a.chunks = (int)((bytes + (int64_t)NXC_P2P_CHUNK_BYTES - 1) / (int64_t)NXC_P2P_CHUNK_BYTES);
-  if (a.chunks < 1) a.chunks = 1;
-  a.bytes = bytes;
-  a.send = (const char *)send;
-  a.recv = (char *)recv;
-  a.status = q->status;
-  nxc_p2p_allgather_kernel<<<q->world * a.chunks, 256, 0, ctx->stream>>>(a);
+  int chunks = (int)((bytes + (int64_t)NXC_P2P_CHUNK_BYTES - 1) / (int64_t)NXC_P2P_CHUNK_BYTES);
+  if (chunks < 1) chunks = 1;
+  nxc_p2p_allgather_kernel<<<ctx->p2p->world * chunks, 256, 0, ctx->stream>>>(nxc_p2p_args(ctx), chunks, bytes,
+                                                                              (const char *)send, (char *)recv);
   NXC_LAUNCH_CHECK(ctx);
   return NXC_OK;
 }
@@ -310,31 +246,46 @@ static int nccl_dtype(int dt) {
 
 static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op, cudaStream_t stream);
 
-extern "C" nxc_status nxc_allreduce(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+// allgather of the partials (peer memory or NCCL, by size) + the backend's own reduce over the rank
+// axis: what serves payloads above the mailbox slot for dtypes / ops NCCL has no reduction for
+// (int16, uint16, fp8, complex prod) and keeps float max / min NaN-sticky
+static nxc_status allreduce_by_gather(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
   const int64_t bytes = count * nxc_elem_size(dtype);
-  if (ctx->p2p && count > 0 && bytes > 0 && (size_t)bytes <= NXC_P2P_SLOT_BYTES && op >= 0 && op <= NXC_RMIN &&
-      nccl_dtype(dtype) >= 0 && dtype != NXC_BOOL) {
-    // gather the partials over peer memory, fold them in rank order with the backend's reduce
-    void *g = NULL;
-    nxc_status s = nxc_alloc(ctx, (size_t)bytes * ctx->world, &g);
-    if (s) return s;
-    s = nxc_p2p_allgather(ctx, buf, g, bytes);
-    if (!s) {
-      nxc_tensor in, out;
-      memset(&in, 0, sizeof in);
-      memset(&out, 0, sizeof out);
-      in.data = g; in.dtype = dtype; in.ndim = 2;
-      in.shape[0] = ctx->world; in.shape[1] = count; in.strides[0] = count; in.strides[1] = 1;
-      out.data = buf; out.dtype = dtype; out.ndim = 1; out.shape[0] = count; out.strides[0] = 1;
-      const int axis = 0;
-      s = nxc_reduce(ctx, op, &out, &in, &axis, 1);
-    }
-    nxc_status f = nxc_free(ctx, g);
-    return s ? s : f;
+  void *g = NULL;
+  nxc_status s = nxc_alloc(ctx, (size_t)bytes * ctx->world, &g);
+  if (s) return s;
+  s = nxc_allgather(ctx, buf, g, bytes);
+  if (!s) {
+    nxc_tensor in, out;
+    memset(&in, 0, sizeof in);
+    memset(&out, 0, sizeof out);
+    in.data = g; in.dtype = dtype; in.ndim = 2;
+    in.shape[0] = ctx->world; in.shape[1] = count; in.strides[0] = count; in.strides[1] = 1;
+    out.data = buf; out.dtype = dtype; out.ndim = 1; out.shape[0] = count; out.strides[0] = 1;
+    const int axis = 0;
+    s = nxc_reduce(ctx, op, &out, &in, &axis, 1);
   }
+  nxc_status f = nxc_free(ctx, g);
+  return s ? s : f;
+}
+
+extern "C" nxc_status nxc_allreduce(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+  NXC_TRACE(ctx, "nxc_allreduce");
+  nxc_status s = dist_usable(ctx);
+  if (s) return s;
+  if (op < 0 || op > NXC_RMIN || !nxc_valid_dtype(dtype) || nxc_is_packed(dtype)) return NXC_ERR_UNSUPPORTED_DTYPE;
+  if (count <= 0) return NXC_OK;
+  const int64_t bytes = count * nxc_elem_size(dtype);
+  // one kernel: exchange over peer memory + fold in rank order (nxc_dist_fold.cu)
+  if (ctx->p2p && (size_t)bytes <= NXC_P2P_SLOT_BYTES) return nxc_p2p_allreduce_fused(ctx, buf, count, dtype, op);
+  const bool is_float = (nxc_dtype_class(dtype) & (NXC_CLS_FLOAT | NXC_CLS_COMPLEX)) != 0;
+  const bool nccl_can = nccl_dtype(dtype) >= 0 || ((dtype == NXC_C32 || dtype == NXC_C64) && op == NXC_SUM);
+  if (!nccl_can || dtype == NXC_BOOL || (is_float && (op == NXC_RMAX || op == NXC_RMIN)))
+    return allreduce_by_gather(ctx, buf, count, dtype, op);
   return allreduce_on(ctx, buf, count, dtype, op, ctx->stream);
 }
 extern "C" nxc_status nxc_allreduce_async(nxc_ctx *ctx, void *buf, int64_t count, int dtype, int op) {
+  NXC_TRACE(ctx, "nxc_allreduce_async");
   nxc_status s = nxc_side_streams(ctx);
   if (s) return s;
   NXC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -362,7 +313,9 @@ static nxc_status allreduce_on(nxc_ctx *ctx, void *buf, int64_t count, int dtype
 }
 
 extern "C" nxc_status nxc_allgather(nxc_ctx *ctx, const void *send, void *recv, int64_t bytes_per_rank) {
-  if (!ctx->nccl_comm) { snprintf(ctx->err, sizeof ctx->err, "%s: nxc_dist_init not called", NXC_ERR_NCCL); return NXC_ERR_NCCL; }
+  NXC_TRACE(ctx, "nxc_allgather");
+  nxc_status us = dist_usable(ctx);
+  if (us) return us;
   if (ctx->p2p && bytes_per_rank > 0 && (size_t)bytes_per_rank <= NXC_P2P_SLOT_BYTES)
     return nxc_p2p_allgather(ctx, send, recv, bytes_per_rank);
   ncclResult_t r = g_nccl.AllGather(send, recv, (size_t)bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);

@@ -372,6 +372,7 @@ static nxc_status nxc_fft_fail(nxc_ctx *ctx, nxc_status s) {
 // fft / ifft (reference: nx_c_fft_run, nx_c_fft.c:940-955; dtype gate nx_c_fft.c:1166)
 extern "C" nxc_status nxc_fft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes,
                               int inverse) {
+  NXC_TRACE(ctx, "nxc_fft");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_fft_fail(ctx, s);
   if (in->dtype != NXC_C32 && in->dtype != NXC_C64) return nxc_fft_fail(ctx, NXC_ERR_BAD_KIND);
@@ -395,6 +396,7 @@ extern "C" nxc_status nxc_fft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_ten
 
 // rfft (reference: nx_c_rfft_run, nx_c_fft.c:958-983)
 extern "C" nxc_status nxc_rfft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes) {
+  NXC_TRACE(ctx, "nxc_rfft");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_fft_fail(ctx, s);
   if ((in->dtype != NXC_F32 && in->dtype != NXC_F64) || (out->dtype != NXC_C32 && out->dtype != NXC_C64))
@@ -424,6 +426,7 @@ extern "C" nxc_status nxc_rfft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_te
 // irfft (reference: nx_c_irfft_run, nx_c_fft.c:1029-1143). s_last <= 0 infers 2*(half-1).
 extern "C" nxc_status nxc_irfft(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, const int *axes, int n_axes,
                                 int64_t s_last) {
+  NXC_TRACE(ctx, "nxc_irfft");
   nxc_status st;
   if ((st = nxc_check_tensor(in)) || (st = nxc_check_tensor(out))) return nxc_fft_fail(ctx, st);
   if ((in->dtype != NXC_C32 && in->dtype != NXC_C64) || (out->dtype != NXC_F32 && out->dtype != NXC_F64))

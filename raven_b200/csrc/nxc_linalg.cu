@@ -322,6 +322,8 @@ static nxc_status nxc_la_fail(nxc_ctx *ctx, nxc_status s) {
   }
 
 extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int upper) {
+  NXC_TRACE(ctx, "nxc_cholesky");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_cholesky (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) return nxc_la_fail(ctx, s);
   if (in->ndim < 2 || out->ndim != in->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
@@ -359,6 +361,8 @@ extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nx
 
 extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a, const nxc_tensor *b,
                                            int flags) {
+  NXC_TRACE(ctx, "nxc_triangular_solve");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_triangular_solve (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(a)) || (s = nxc_check_tensor(b)) || (s = nxc_check_tensor(out))) return nxc_la_fail(ctx, s);
   if (a->ndim < 2 || b->ndim != a->ndim || out->ndim != b->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
@@ -402,6 +406,8 @@ extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, 
 }
 
 extern "C" nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r, const nxc_tensor *in, int reduced) {
+  NXC_TRACE(ctx, "nxc_qr");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_qr (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(q)) || (s = nxc_check_tensor(r))) return nxc_la_fail(ctx, s);
   if (in->ndim < 2 || q->ndim != in->ndim || r->ndim != in->ndim) return nxc_la_fail(ctx, NXC_LA_SHAPE);
@@ -447,6 +453,8 @@ static const char NXC_LA_NO_CONVERGE[] = "eigenvalue iteration did not converge"
 // eigh / eigvalsh (reference: caml_nx_c_eigh, nx_c_eigh.c; veneer backend_c/nx_backend.ml:627-648).
 // `w` is f64 [batch, n]; `v` (input dtype, input shape) is written only when vectors != 0.
 extern "C" nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tensor *v, const nxc_tensor *in, int vectors) {
+  NXC_TRACE(ctx, "nxc_eigh");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_eigh (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(w))) return nxc_la_fail(ctx, s);
   if (in->ndim < 2 || w->ndim != in->ndim - 1) return nxc_la_fail(ctx, NXC_LA_SHAPE);
@@ -579,6 +587,8 @@ static nxc_status nxc_la_status3(nxc_ctx *ctx, int *dev_status) {
 // full is read off each output's shape, as the reference does.
 extern "C" nxc_status nxc_svd(nxc_ctx *ctx, const nxc_tensor *u, const nxc_tensor *sv, const nxc_tensor *vt,
                               const nxc_tensor *in) {
+  NXC_TRACE(ctx, "nxc_svd");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_svd (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(u)) || (s = nxc_check_tensor(sv)) || (s = nxc_check_tensor(vt)))
     return nxc_la_fail(ctx, s);
@@ -656,6 +666,8 @@ static const char NXC_EIG_TOO_LARGE[] = "matrix dimension exceeds eig limit";
 // eig / eigvals (reference: caml_nx_c_eig, nx_c_eig.c:1310-1326; driver nx_c_eig_run :1195-1298; veneer
 // backend_c/nx_backend.ml:679-707). w is c64 [batch, n]; v c64 [batch, n, n], written only when vectors != 0.
 extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tensor *v, const nxc_tensor *in, int vectors) {
+  NXC_TRACE(ctx, "nxc_eig");
+  if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_eig (reads a status word back)");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(w))) return nxc_la_fail(ctx, s);
   if (vectors && (s = nxc_check_tensor(v))) return nxc_la_fail(ctx, s);

@@ -343,9 +343,11 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
     typedef std::integral_constant<bool, false> F_;
     typedef std::integral_constant<bool, true> T_;
     const bool any_neg = na | nb | nc;
-    if (!any_neg && !(ba | bb | bc)) run_all(F_(), F_(), F_(), F_());
-    else if (!any_neg && bb && !ba && !bc) run_all(F_(), T_(), F_(), F_());
-    else if (!any_neg && ba && !bb && !bc) run_all(T_(), F_(), F_(), F_());
+    // a scalar item (VW == 1) is loaded and consumed the same way whatever the flags: one body
+    // (the straight-line variants of it were identical code, a third of libnxcuda.so's size)
+    if (VW > 1 && !any_neg && !(ba | bb | bc)) run_all(F_(), F_(), F_(), F_());
+    else if (VW > 1 && !any_neg && bb && !ba && !bc) run_all(F_(), T_(), F_(), F_());
+    else if (VW > 1 && !any_neg && ba && !bb && !bc) run_all(T_(), F_(), F_(), F_());
     else {
       // anything else (a reversed run, several broadcast operands): flags stay run-time values
 #pragma unroll

@@ -62,6 +62,7 @@ static nxc_status same_shape(const nxc_tensor *const *ops, int nop) {
 }
 
 extern "C" nxc_status nxc_map1(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *a) {
+  NXC_TRACE(ctx, "nxc_map1");
   const nxc_tensor *ops[2] = {out, a};
   nxc_status s = check_ops(ops, 2);
   if (s) return fail(ctx, s);
@@ -86,6 +87,7 @@ extern "C" nxc_status nxc_map1(nxc_ctx *ctx, int op, const nxc_tensor *out, cons
 
 extern "C" nxc_status nxc_map2(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *a,
                                const nxc_tensor *b) {
+  NXC_TRACE(ctx, "nxc_map2");
   const nxc_tensor *ops[3] = {out, a, b};
   nxc_status s = check_ops(ops, 3);
   if (s) return fail(ctx, s);
@@ -105,6 +107,7 @@ extern "C" nxc_status nxc_map2(nxc_ctx *ctx, int op, const nxc_tensor *out, cons
 
 extern "C" nxc_status nxc_cmp(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *a,
                               const nxc_tensor *b) {
+  NXC_TRACE(ctx, "nxc_cmp");
   const nxc_tensor *ops[3] = {out, a, b};
   nxc_status s = check_ops(ops, 3);
   if (s) return fail(ctx, s);
@@ -123,6 +126,7 @@ extern "C" nxc_status nxc_cmp(nxc_ctx *ctx, int op, const nxc_tensor *out, const
 
 extern "C" nxc_status nxc_where(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *cond,
                                 const nxc_tensor *a, const nxc_tensor *b) {
+  NXC_TRACE(ctx, "nxc_where");
   const nxc_tensor *ops[4] = {out, cond, a, b};
   nxc_status s = check_ops(ops, 4);
   if (s) return fail(ctx, s);
@@ -138,6 +142,7 @@ extern "C" nxc_status nxc_where(nxc_ctx *ctx, const nxc_tensor *out, const nxc_t
 }
 
 extern "C" nxc_status nxc_cast(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a) {
+  NXC_TRACE(ctx, "nxc_cast");
   const nxc_tensor *ops[2] = {out, a};
   nxc_status s;
   for (int k = 0; k < 2; k++)
@@ -161,6 +166,7 @@ nxc_status nxc_cast_group(nxc_ctx *ctx, int src, int dst, const NxcMapPlan &p) {
 }
 
 extern "C" nxc_status nxc_copy(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a) {
+  NXC_TRACE(ctx, "nxc_copy");
   const nxc_tensor *ops[2] = {out, a};
   if (nxc_valid_dtype(out->dtype) && nxc_is_packed(out->dtype) && a->dtype == out->dtype && out->ndim <= NXC_MAX_NDIM &&
       a->ndim <= NXC_MAX_NDIM)
@@ -177,6 +183,7 @@ extern "C" nxc_status nxc_copy(nxc_ctx *ctx, const nxc_tensor *out, const nxc_te
 }
 
 extern "C" nxc_status nxc_fill(nxc_ctx *ctx, const nxc_tensor *out, const void *scalar) {
+  NXC_TRACE(ctx, "nxc_fill");
   const nxc_tensor *ops[1] = {out};
   nxc_status s = check_ops(ops, 1);
   if (s) return fail(ctx, s);

@@ -75,6 +75,7 @@ static nxc_status nxc_matmul_tc_packed(nxc_ctx *ctx, const NxcMatmulProblem &q, 
 
 extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_tensor *A,
                                  const nxc_tensor *B) {
+  NXC_TRACE(ctx, "nxc_matmul");
   nxc_status s = NXC_OK;
   NxcMatmulProblem p;
   if ((s = nxc_check_tensor(A)) || (s = nxc_check_tensor(B)) || (s = nxc_check_tensor(C))) goto fail;
@@ -93,22 +94,28 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
     p.n = B->shape[B->ndim - 1];
     if (p.k != B->shape[B->ndim - 2]) { s = NXC_ERR_SHAPE; goto fail; }
     if (C->shape[nd - 2] != p.m || C->shape[nd - 1] != p.n) { s = NXC_ERR_SHAPE; goto fail; }
+    // Batch dims broadcast numpy-style: operands are right-aligned against the output's rank, a
+    // missing or size-1 dim repeats (stride 0), anything else must agree; the output has the
+    // broadcast extent and may not alias itself (rules: nx_c_matmul.c:895-926).
     p.batch_nd = nd - 2;
     p.nbatch = 1;
-    const int a_bo = nd - A->ndim, b_bo = nd - B->ndim;
+    struct BatchDim { int64_t extent, stride; };
+    auto batch_dim = [nd](const nxc_tensor *t, int i) -> BatchDim {
+      const int j = i - (nd - t->ndim);  // this operand's own dim index, negative = absent
+      if (j < 0 || t->shape[j] == 1) return {1, 0};
+      return {t->shape[j], t->strides[j]};
+    };
     for (int i = 0; i < p.batch_nd; i++) {
-      int64_t sa = 1, sb = 1, sta = 0, stb = 0;
-      if (i >= a_bo) { sa = A->shape[i - a_bo]; sta = A->strides[i - a_bo]; }
-      if (i >= b_bo) { sb = B->shape[i - b_bo]; stb = B->strides[i - b_bo]; }
-      if (sa != sb && sa != 1 && sb != 1) { s = NXC_ERR_SHAPE; goto fail; }
-      const int64_t sz = sa > sb ? sa : sb;
-      if (C->shape[i] != sz) { s = NXC_ERR_SHAPE; goto fail; }
-      p.bshape[i] = sz;
-      p.as_[i] = (sa == 1) ? 0 : sta;
-      p.bs_[i] = (sb == 1) ? 0 : stb;
+      const BatchDim da = batch_dim(A, i), db = batch_dim(B, i);
+      const int64_t extent = da.extent > db.extent ? da.extent : db.extent;
+      const bool agree = da.extent == db.extent || da.extent == 1 || db.extent == 1;
+      if (!agree || C->shape[i] != extent) { s = NXC_ERR_SHAPE; goto fail; }
+      if (extent > 1 && C->strides[i] == 0) { s = NXC_ERR_OUT_ALIASED; goto fail; }
+      p.bshape[i] = extent;
+      p.as_[i] = da.stride;
+      p.bs_[i] = db.stride;
       p.cs_[i] = C->strides[i];
-      if (sz > 1 && p.cs_[i] == 0) { s = NXC_ERR_OUT_ALIASED; goto fail; }
-      p.nbatch *= sz;
+      p.nbatch *= extent;
     }
     if (p.m == 0 || p.n == 0 || p.nbatch == 0) return NXC_OK;
     p.a_rs = A->strides[A->ndim - 2]; p.a_cs = A->strides[A->ndim - 1];

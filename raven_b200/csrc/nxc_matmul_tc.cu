@@ -624,15 +624,14 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
             ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->mm_attr_set) {  // per context = per device; a function attribute is device state
     NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<false>::SMEM_BYTES));
     NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true>::SMEM_BYTES));
     NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true, true>::SMEM_BYTES));
-    attr_set = true;
+    ctx->mm_attr_set = 1;
   }
   const int64_t tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
   if (!pair) {

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "nxc_common.cuh"
+#include "nxc_tanh64.cuh"
 
 // ---- libm by compute type -----------------------------------------------------
 #define NXC_M1(name, ffn, dfn)                                         \
@@ -27,10 +28,9 @@ __device__ __forceinline__ double m_tan(double x) { return tan(x); }
 __device__ __forceinline__ float m_sinh(float x) { return (float)sinh((double)x); }
 __device__ __forceinline__ double m_sinh(double x) { return sinh(x); }
 __device__ __forceinline__ float m_tanh(float x) { return (float)tanh((double)x); }
-// f64 tanh is CUDA's: measured 3 ulp from glibc at worst over 2^20 samples (every other
-// f64 op stays within 2); an fdlibm-style expm1 formulation gave identical bits, so the
-// residual is libdevice's expm1/exp itself. Stated as the one 3-ulp exception in DESIGN.md.
-__device__ __forceinline__ double m_tanh(double x) { return tanh(x); }
+// f64 tanh: libdevice's is 3 ulp from glibc at worst; nxc_tanh64.cuh restates glibc's own
+// expm1-based algorithm with its fused multiply-adds explicit (bit-identical on 40 M samples).
+__device__ __forceinline__ double m_tanh(double x) { return nxc_t64::tanh64(x); }
 NXC_M1(trunc, truncf, trunc) NXC_M1(ceil, ceilf, ceil) NXC_M1(floor, floorf, floor)
 NXC_M1(round, roundf, round) NXC_M1(erf, erff, erf) NXC_M1(fabs, fabsf, fabs)
 #undef NXC_M1

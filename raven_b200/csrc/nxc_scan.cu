@@ -81,6 +81,7 @@ template <int OP, int DT> struct ScanLaunch<OP, DT, false> {
   case OPC: { NXC_DISPATCH_DTYPE(dt, { st = ScanLaunch<OPC, DT, ScanP<OPC, DT>::ok>::go(ctx, out, in, a); }) } break;
 
 extern "C" nxc_status nxc_scan(nxc_ctx *ctx, int op, const nxc_tensor *out, const nxc_tensor *in, int axis) {
+  NXC_TRACE(ctx, "nxc_scan");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) goto fail;
   {

@@ -166,6 +166,7 @@ static nxc_status sort_run(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor
 
 extern "C" nxc_status nxc_sort(nxc_ctx *ctx, int is_arg, const nxc_tensor *out, const nxc_tensor *in, int axis,
                                int descending) {
+  NXC_TRACE(ctx, "nxc_sort");
   nxc_status s;
   if ((s = nxc_check_tensor(in)) || (s = nxc_check_tensor(out))) goto fail;
   {

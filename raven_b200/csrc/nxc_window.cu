@@ -124,6 +124,7 @@ static nxc_status win_fail(nxc_ctx *ctx, nxc_status s) {
 extern "C" nxc_status nxc_unfold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int K,
                                  const int64_t *kernel, const int64_t *stride, const int64_t *dilation,
                                  const int64_t *padding_flat) {
+  NXC_TRACE(ctx, "nxc_unfold");
   nxc_status s;
   if ((s = nxc_check_tensor(out)) || (s = nxc_check_tensor(in))) return win_fail(ctx, s);
   if (nxc_is_packed(out->dtype)) return win_fail(ctx, NXC_ERR_PACKED);
@@ -160,6 +161,7 @@ extern "C" nxc_status nxc_unfold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_
 extern "C" nxc_status nxc_fold(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int K,
                                const int64_t *output_size, const int64_t *kernel, const int64_t *stride,
                                const int64_t *dilation, const int64_t *padding_flat) {
+  NXC_TRACE(ctx, "nxc_fold");
   nxc_status s;
   if ((s = nxc_check_tensor(out)) || (s = nxc_check_tensor(in))) return win_fail(ctx, s);
   const int dt = out->dtype;

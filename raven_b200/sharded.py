@@ -15,10 +15,12 @@ reference code. What it must preserve is the single-device ANSWER:
                     promise NaN propagation, and the reference's do (nx_c_fold.c:80-89),
                     so the partials are allgathered and folded locally with the
                     backend's own NaN-sticky max/min.
-  argmax/argmin     each rank emits (local extreme value, local index + slab offset);
-                    both are allgathered and the winner is chosen by the backend's own
-                    argreduce over the gathered values, ties and NaNs resolving to
-                    the lowest rank = the lowest global index, i.e. bit-exact.
+  argmax/argmin     each rank emits (local extreme value, local index + slab offset); the
+                    winner is chosen by the backend's own first-index / first-NaN rule, ties
+                    and NaNs resolving to the lowest rank = the lowest global index, i.e.
+                    bit-exact. With the peer-memory mailboxes mapped this is ONE kernel after
+                    the local argreduce (nxc_argreduce_exchange: push, wait, pick); otherwise
+                    two all-gathers and the backend's argreduce over the gathered values.
   axes not including the sharded axis -> outputs are disjoint: allgather only.
   batch-leading matmul -> independent per rank; allgather of C only on request.
 
@@ -90,6 +92,24 @@ class NcclComm:
               self.ctx._lib.nxc_allgather(self.ctx.ptr, t.buffer.ptr, out.buffer.ptr, nbytes))
         return out
 
+    def argreduce_exchange(self, x_local: B.Tensor, local_idx: B.Tensor, is_max: bool, axis: int, slab_offset: int):
+        """The cross-rank finish of an argmax / argmin along the sharded axis as ONE kernel over the
+        peer-memory mailboxes (nxc_argreduce_exchange); None when that path does not apply (mailboxes
+        not mapped, more outputs than a mailbox slot holds) and the caller should use all-gathers."""
+        lib = self.ctx._lib
+        n = 1
+        for s in local_idx.shape:
+            n *= s
+        if n == 0 or n > int(lib.nxc_argreduce_exchange_max_outputs(self.ctx.ptr)):
+            return None
+        local_idx = B.contiguous(local_idx)
+        out = B.buffer(self.ctx, D.int32, local_idx.shape)
+        do, dx, di = out._desc(), x_local._desc(), local_idx._desc()
+        check(self.ctx.ptr, "argmax" if is_max else "argmin",
+              lib.nxc_argreduce_exchange(self.ctx.ptr, 1 if is_max else 0, ctypes.byref(do), ctypes.byref(dx),
+                                         ctypes.byref(di), int(axis), int(slab_offset)))
+        return out
+
     def close(self):
         self.ctx._lib.nxc_dist_finalize(self.ctx.ptr)
 
@@ -135,6 +155,11 @@ def sharded_argreduce(x_local, is_max: bool, axis: int, slab_offset: int, comm, 
         g = comm.allgather(fn(x_local, axis, False))
         shp = tuple(g.shape)
         return backend.reshape(g, (shp[0] * shp[1],) + shp[2:]) if len(shp) >= 2 else g
+    if hasattr(comm, "argreduce_exchange"):
+        # local argreduce + one exchange-and-pick kernel over peer memory (2-3 launches in all)
+        out = comm.argreduce_exchange(x_local, fn(x_local, 0, False), is_max, 0, slab_offset)
+        if out is not None:
+            return out
     idxk = fn(x_local, 0, True)
     idx = backend.reshape(idxk, tuple(idxk.shape[1:]))
     # the local extreme is read back at the winning index (one element per output) instead of
@@ -186,6 +211,69 @@ class GradBucketReducer:
             inv = be.full(t.context, t.dtype, [], 1.0 / self.comm.world)
             out.append(be.mul(t, be.expand(inv, t.shape) if len(t.shape) else inv))
         self.leaves = []
+        return out
+
+
+class FlatBucketReducer:
+    """Data-parallel gradient averaging in flat buckets (what a pmap'ed step's psum lowers to,
+    reference: packages/rune/lib/jit.ml:181-190): `push(name, leaf)` as the backward pass completes
+    a gradient leaf; once `bucket_bytes` of leaves of one dtype have gathered they are concatenated
+    into ONE buffer whose sum-allreduce starts on the communication stream (NCCL over NVLink) while
+    the backward pass goes on. `finish()` flushes the rest, makes the stream wait, scales each
+    bucket by 1/world once and returns {name: view of the averaged leaf}. A few large collectives
+    instead of one per leaf: a GPT-2-small step has 148 leaves, most of them a few KB."""
+
+    def __init__(self, comm, bucket_bytes=64 << 20, backend=B):
+        self.comm, self.backend, self.bucket_bytes = comm, backend, int(bucket_bytes)
+        self.open = {}      # dtype name -> [(name, leaf)]
+        self.open_bytes = {}
+        self.buckets = []   # (flat tensor, [(name, shape, numel)])
+
+    def push(self, name, t):
+        key = t.dtype.name
+        self.open.setdefault(key, []).append((name, t))
+        n = 1
+        for s in t.shape:
+            n *= s
+        self.open_bytes[key] = self.open_bytes.get(key, 0) + n * t.dtype.itemsize
+        if self.open_bytes[key] >= self.bucket_bytes:
+            self._flush(key)
+
+    def _flush(self, key):
+        be = self.backend
+        leaves = self.open.pop(key, [])
+        self.open_bytes.pop(key, None)
+        if not leaves:
+            return
+        meta, flats = [], []
+        for name, t in leaves:
+            n = 1
+            for s in t.shape:
+                n *= s
+            meta.append((name, tuple(t.shape), n))
+            flats.append(be.reshape(be.contiguous(t), [n]))
+        flat = flats[0] if len(flats) == 1 else be.cat(flats, 0)
+        if hasattr(self.comm, "allreduce_async"):
+            self.comm.allreduce_async(flat, "sum")
+        else:
+            flat = self.comm.allreduce(flat, "sum")
+        self.buckets.append((flat, meta))
+
+    def finish(self):
+        be = self.backend
+        for key in list(self.open):
+            self._flush(key)
+        if hasattr(self.comm, "wait"):
+            self.comm.wait()
+        out = {}
+        for flat, meta in self.buckets:
+            inv = be.expand(be.reshape(be.full(flat.context, flat.dtype, [], 1.0 / self.comm.world), [1]), list(flat.shape))
+            avg = be.mul(flat, inv)
+            lo = 0
+            for name, shape, n in meta:
+                out[name] = be.reshape(be.shrink(avg, [(lo, lo + n)]), list(shape))
+                lo += n
+        self.buckets = []
         return out
 
 

@@ -257,3 +257,29 @@ def assert_close(dtype: str, got: np.ndarray, want: np.ndarray, rel: float, abs_
     tol = abs_ + rel * np.abs(np.where(both_nan | same_inf, 0, w))
     ok = (err <= tol) | both_nan | same_inf
     assert ok.all(), f"{what}: {dtype} got {g[~ok][:4]} want {w[~ok][:4]} (rel {rel})"
+
+
+def storage_ulp(dtype, x):
+    """Spacing of the 16-bit storage type at |x| (float64 array)."""
+    mant, emin = {"bf16": (7, -126), "f16": (10, -14)}[dtype]
+    ax = np.abs(np.asarray(x, dtype=np.float64))
+    e = np.floor(np.log2(np.where(ax > 0, ax, 1.0)))
+    e = np.where(ax > 0, np.maximum(e, emin), emin)
+    return np.exp2(e - mant)
+
+
+def assert_gemm_16bit(dtype, got, want, absprod, k, what):
+    """bf16 / f16 products, ELEMENTWISE: the reference accumulates in f32 and rounds once
+    (nx_c_matmul.c:12-28); so does the tensor-core path, in another order. Two f32 sums of the same
+    K products differ by at most ~2 K eps32 sum|a||b| (which matters only where the sum cancels),
+    and the single rounding to storage can then land on the neighbouring value: 1 storage ulp of the
+    reference's element plus that accumulation slack, per element -- no tolerance relative to the
+    largest element of C."""
+    g, w = storage_to_float(dtype, got), storage_to_float(dtype, want)
+    bound = storage_ulp(dtype, w) + 2.0 * k * 2.0 ** -24 * absprod
+    err = np.abs(g - w)
+    ok = (err <= bound) | (np.isnan(g) & np.isnan(w)) | (g == w)
+    if not ok.all():
+        i = np.unravel_index(np.argmax(np.where(ok, 0, err / bound)), err.shape)
+        raise AssertionError(f"{what}: {dtype} element {i}: got {g[i]!r} want {w[i]!r}, |diff| {err[i]:.3e} > 1 ulp + "
+                             f"slack = {bound[i]:.3e} ({int((~ok).sum())} of {ok.size} elements)")

@@ -1,0 +1,77 @@
+"""The Kaun GPT-2 training step (BASELINE.json configs[4]) replayed through the CUDA backend against
+the SAME op sequence replayed through the reference's C backend (tests/backend_double.py): loss
+trajectory and updated parameters over several SGD / AdamW steps, float32 and the bfloat16
+astype sandwich; and the captured step (CUDA graph) against the eager one, bit for bit.
+
+Sizes are a tiny GPT-2 (2 layers, 4 heads, 32 wide, vocab 257 -- an odd row pitch like 50257's)
+so the oracle finishes in seconds; the 124M shapes are exercised op by op in
+tests/test_gpu_model_shapes.py and end to end by bench.py / tools/gpt2_step.py."""
+import numpy as np
+import pytest
+
+import raven_b200.backend as B
+from tests import harness as H
+from tests.backend_double import Ctx, OracleBackend
+from tools import gpt2_step as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(be, ctx, host, grid, opt, compute, steps, capture=False):
+    tr = G.Trainer(be, ctx, G.GPT2_TINY, grid.shape[0], grid.shape[1] - 1, opt=opt, lr=1e-2, compute=compute,
+                   host_params={k: v.copy() for k, v in host.items()})
+    tr.set_batch(grid[:, :-1], grid[:, 1:])
+    losses = []
+    graph = None
+    for i in range(steps):
+        tr.pre_step()
+        if capture and i == 1:
+            with ctx.capture() as graph:
+                loss = tr.step_body()
+            graph.launch()
+        elif graph is not None:
+            graph.launch()
+        else:
+            loss = tr.step_body()
+        losses.append(float(np.asarray(be.to_numpy(loss), dtype=np.float64)))
+    params = {k: np.asarray(be.to_numpy(v)) for k, v in tr.params.items()}
+    if graph is not None:
+        graph.close()
+    return losses, params
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adamw"])
+def test_f32_step_matches_the_reference_backend(ctx, opt):
+    rng = np.random.default_rng(0)
+    grid = rng.integers(0, G.GPT2_TINY["vocab"], (3, 17))
+    host = G.init_params_host(G.GPT2_TINY, seed=4)
+    want_l, want_p = _run(OracleBackend(), Ctx(), host, grid, opt, None, 4)
+    got_l, got_p = _run(B, ctx, host, grid, opt, None, 4)
+    assert np.allclose(got_l, want_l, rtol=1e-5, atol=1e-6), (got_l, want_l)
+    assert got_l[-1] < got_l[0]
+    for k in want_p:
+        # four steps of f32 arithmetic in two summation orders: 1e-4 of the parameter scale
+        scale = float(np.abs(want_p[k]).max()) or 1.0
+        assert np.abs(got_p[k].astype(np.float64) - want_p[k].astype(np.float64)).max() <= 1e-4 * scale, k
+
+
+def test_bf16_sandwich_step_tracks_the_reference_backend(ctx):
+    rng = np.random.default_rng(1)
+    grid = rng.integers(0, G.GPT2_TINY["vocab"], (2, 17))
+    host = G.init_params_host(G.GPT2_TINY, seed=5)
+    want_l, _ = _run(OracleBackend(), Ctx(), host, grid, "sgd", "bf16", 3)
+    got_l, _ = _run(B, ctx, host, grid, "sgd", "bf16", 3)
+    # bf16 activations: the two backends round intermediate sums differently (2^-8 relative each)
+    assert np.allclose(got_l, want_l, rtol=2e-2), (got_l, want_l)
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adamw"])
+def test_captured_step_equals_the_eager_step(ctx, opt):
+    rng = np.random.default_rng(2)
+    grid = rng.integers(0, G.GPT2_TINY["vocab"], (2, 9))
+    host = G.init_params_host(G.GPT2_TINY, seed=6)
+    eager_l, eager_p = _run(B, ctx, host, grid, opt, None, 5)
+    graph_l, graph_p = _run(B, ctx, host, grid, opt, None, 5, capture=True)
+    assert eager_l == graph_l, (eager_l, graph_l)
+    for k in eager_p:
+        assert np.array_equal(H.raw(eager_p[k]), H.raw(graph_p[k])), k

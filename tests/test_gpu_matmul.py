@@ -4,8 +4,10 @@ transposed lhs / rhs / both, offsets, batched and batch-broadcast operands
 
 Tolerances: integers bit-exact (accumulation is modular); f64 1e-11*(k+1) and f32
 1e-5*(k+1) relative to the row/column magnitude as the contract states; bf16/f16
-on the tcgen05 path 1e-3 relative against an f32-accumulated product of the same
-stored inputs plus one storage rounding (north_star).
+on the tcgen05 path ELEMENTWISE within one storage ulp of the reference's f32-accumulated,
+once-rounded element, plus the reordering slack of an f32 sum of K products where the sum
+cancels (assert_gemm_16bit) -- tighter than north_star's 1e-3 relative on every element that
+does not cancel, and never relative to the largest element of C.
 """
 import numpy as np
 import pytest
@@ -40,7 +42,16 @@ def _tol(dtype, k):
         return 1e-11 * (k + 1)
     if dtype == "f32" or dtype == "c32":
         return 1e-5 * (k + 1) ** 0.5
-    return {"f16": 2e-3, "bf16": 1.6e-2, "f8e4m3": 0.13, "f8e5m2": 0.26}[dtype]
+    return {"f8e4m3": 0.13, "f8e5m2": 0.26}[dtype]
+
+
+storage_ulp, assert_gemm_16bit = H.storage_ulp, H.assert_gemm_16bit
+
+
+def _absprod(dtype, a, b):
+    fa = np.abs(H.storage_to_float(dtype, a.numpy()))
+    fb = np.abs(H.storage_to_float(dtype, b.numpy()))
+    return np.matmul(fa, fb)
 
 
 def _check(ctx, oracle, dtype, a, b, what, k):
@@ -48,6 +59,8 @@ def _check(ctx, oracle, dtype, a, b, what, k):
     got = H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, b)))
     if dtype in H.INTS:
         H.assert_same(dtype, got, want, what=what)
+    elif dtype in ("bf16", "f16"):
+        assert_gemm_16bit(dtype, got, want, _absprod(dtype, a, b), k, what)
     else:
         scale = float(np.max(np.abs(H.storage_to_float(dtype, want) if dtype not in H.COMPLEX else want))) or 1.0
         H.assert_close(dtype, got, want, rel=_tol(dtype, k), abs_=_tol(dtype, k) * scale, what=what)
@@ -159,19 +172,27 @@ def test_matmul_tc_tile_modes(ctx, oracle, dtype, pair_mode):
             for name, (x, y) in {"nn": (a, b), "tn": (at, b), "nt": (a, bt), "tt": (at, bt)}.items():
                 want = oracle.matmul(x, y).numpy()
                 got = H.download(B.matmul(H.upload(ctx, x), H.upload(ctx, y)))
+                what = f"{dtype}/pair={pair_mode}/{(m, k, n)}/{name}"
+                if dtype in ("bf16", "f16"):
+                    assert_gemm_16bit(dtype, got, want, _absprod(dtype, x, y), k, what)
+                    continue
                 wf, gf = H.storage_to_float(st, want), H.storage_to_float(st, got)
                 scale = float(np.max(np.abs(wf))) or 1.0
                 tol = 1e-3 if dtype == "tf32" else _tol(dtype, k)
                 err = float(np.max(np.abs(gf - wf)))
-                assert err <= tol * scale, f"{dtype}/pair={pair_mode}/{(m, k, n)}/{name}: err {err} scale {scale}"
+                assert err <= tol * scale, f"{what}: err {err} scale {scale}"
         # batched: [3, m, k] x [k, n] (broadcast rhs) and [3, m, k] x [3, k, n]
         m, k, n = 384, 96, 320
         A = H.to_storage(st, rng.standard_normal((3, m, k)) / np.sqrt(k))
         Bm = H.to_storage(st, rng.standard_normal((3, k, n)))
         a = H.HostView(A.reshape(-1).copy(), st, [3, m, k])
         for b in (H.HostView(Bm[0].reshape(-1).copy(), st, [k, n]), H.HostView(Bm.reshape(-1).copy(), st, [3, k, n])):
-            want = H.storage_to_float(st, oracle.matmul(a, b).numpy())
-            got = H.storage_to_float(st, H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, b))))
+            want_s = oracle.matmul(a, b).numpy()
+            got_s = H.download(B.matmul(H.upload(ctx, a), H.upload(ctx, b)))
+            if dtype in ("bf16", "f16"):
+                assert_gemm_16bit(dtype, got_s, want_s, _absprod(dtype, a, b), k, f"batched/{dtype}")
+                continue
+            want, got = H.storage_to_float(st, want_s), H.storage_to_float(st, got_s)
             tol = 1e-3 if dtype == "tf32" else _tol(dtype, k)
             assert float(np.max(np.abs(got - want))) <= tol * (float(np.max(np.abs(want))) or 1.0), f"batched/{dtype}"
     finally:
@@ -244,16 +265,14 @@ def test_matmul_tensor_core_path_packs_operands_tma_cannot_describe(ctx, oracle)
         before = ctx.launch_count()
         got = H.download(B.matmul(H.upload(ctx, x), H.upload(ctx, y)))
         assert ctx.launch_count() - before >= 2, name
-        scale = float(np.max(np.abs(H.storage_to_float("bf16", want)))) or 1.0
-        H.assert_close("bf16", got, want, rel=_tol("bf16", k), abs_=_tol("bf16", k) * scale, what=name)
+        assert_gemm_16bit("bf16", got, want, _absprod("bf16", x, y), k, name)
     # batched lhs whose batch stride is not a 16-byte multiple, against a broadcast rhs
     A3 = H.to_storage("bf16", rng.standard_normal((3, 128, k + 1)) / 8)
     a3 = H.HostView(A3.reshape(-1).copy(), "bf16", [3, 128, k + 1]).shrink([(0, 3), (0, 128), (0, k)])
     y = cases["odd pitch"][1]
     want = oracle.matmul(a3, y).numpy()
     got = H.download(B.matmul(H.upload(ctx, a3), H.upload(ctx, y)))
-    scale = float(np.max(np.abs(H.storage_to_float("bf16", want)))) or 1.0
-    H.assert_close("bf16", got, want, rel=_tol("bf16", k), abs_=_tol("bf16", k) * scale, what="batched odd pitch")
+    assert_gemm_16bit("bf16", got, want, _absprod("bf16", a3, y), k, "batched odd pitch")
 
 
 def test_matmul_f32_attention_shaped_batch_runs_as_3xtf32(ctx, oracle):
@@ -295,4 +314,5 @@ def test_matmul_m_major_lhs_with_wide_n_is_packed_and_bit_identical(ctx):
     gf = H.bf16_bits_to_f32(H.download(g)).astype(np.float64)
     want = xf[:, :4].T @ gf
     got = H.bf16_bits_to_f32(via_view[:4]).astype(np.float64)
-    assert np.abs(got - want).max() <= 1.6e-2 * np.abs(want).max()
+    bound = storage_ulp("bf16", want) + 2.0 * k * 2.0 ** -24 * (np.abs(xf[:, :4]).T @ np.abs(gf))
+    assert (np.abs(got - want) <= bound).all(), float(np.max(np.abs(got - want) / bound))
