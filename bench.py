@@ -558,8 +558,11 @@ def main():
         e2e_step()
     sync_all()
     t0 = time.perf_counter()
+    per_step = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         res = e2e_step()
+        per_step.append(round((time.perf_counter() - t1) * 1e3, 1))
     sync_all()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_local = e2e_s
@@ -570,7 +573,7 @@ def main():
     d2h = 3 * nbytes + sum(int(x.nbytes) for x in res)
     e2e = {"value": round(world * step_bytes(n) / e2e_s / 1e9, 2), "unit": "GB/s",
            "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3),
-           "steps": e2e_steps,
+           "steps": e2e_steps, "host_wall_ms_of_each_step": per_step,
            # what limits it: each rank moves this much over its own PCIe link per step, both directions at once
            "pcie_gbs_per_rank": {"h2d": round(2 * nbytes / e2e_local / 1e9, 1), "d2h": round(d2h / e2e_local / 1e9, 1)}}
     # the last step's read-backs are complete (sync_all above drains the device): check all three

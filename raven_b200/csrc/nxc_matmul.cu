@@ -127,6 +127,22 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
     p.b = (const char *)B->data + B->offset * es;
     p.c = (char *)C->data + C->offset * es;
 
+    // x [batch..., m, k] @ W [k, n] -- every Kaun Linear.apply on a [B, T, C] activation (linear.ml:50-52)
+    // -- is ONE product with batch * m rows when the batches of x and of the output follow each
+    // other at the row pitch: fold them, so the kernels see a tall matrix (full tiles, one
+    // launch-worth of work) instead of `batch` short ones (the GPT-2 step at 4 x 64 tokens ran its
+    // linears as 4 products of 64 rows: 24 CTAs on 148 SMs).
+    if (p.nbatch > 1 && p.m > 0) {
+      bool fold = true;
+      int64_t rows = p.m;
+      for (int i = p.batch_nd - 1; i >= 0 && fold; i--) {
+        if (p.bshape[i] == 1) continue;
+        fold = p.bs_[i] == 0 && p.as_[i] == rows * p.a_rs && p.cs_[i] == rows * p.c_rs;
+        rows *= p.bshape[i];
+      }
+      if (fold) { p.m = rows; p.nbatch = 1; p.batch_nd = 0; }
+    }
+
     const bool tc_dtype = (dt == NXC_BF16 || dt == NXC_F16 || (dt == NXC_F32 && ctx->matmul_tf32 == 1));
     if (tc_dtype) {
       // An M-major LEFT operand (a transposed view: the x^T of every dW = x^T g) is consumed in place,
@@ -142,13 +158,15 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
       if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
     }
     // f32 at f32-class accuracy on the tensor cores (3xTF32, nxc_matmul_x3.cu) -- the default for
-    // f32 once the product is a few GFLOP and so worth the two split passes (measured 8192^3: 230
+    // f32 once the product is a quarter GFLOP and so worth the two split passes (a 256 x 768 x 768
+    // linear of the GPT-2 step: 260 us on the CUDA-core kernel, whose 128 x 128 tiles leave most SMs
+    // idle at that size; measured 8192^3: 230
     // vs 30 TFLOP/s; error 2e-6 .. 6e-5 of max |A||B| for K = 1024 .. 8192, inside the classical
     // K*u sgemm bound and 20x inside the reference's own f32 matmul tolerance, 1e-3 rel + 1e-3 abs,
     // backend_c/test/matmul_test.ml:831). Mode "ieee" keeps every f32 product on the CUDA-core
     // kernel (each product and sum rounded to nearest, like the reference's microkernel).
     if (dt == NXC_F32 && (ctx->matmul_tf32 == 0 || ctx->matmul_tf32 == 2) && p.m >= 128 && p.n >= 128 &&
-        2.0 * (double)p.m * (double)p.n * (double)p.k * (double)p.nbatch >= 2147483648.0) {
+        2.0 * (double)p.m * (double)p.n * (double)p.k * (double)p.nbatch >= 268435456.0) {
       s = nxc_matmul_f32x3(ctx, p);
       if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }
     }

@@ -50,9 +50,11 @@ def test_f32_step_matches_the_reference_backend(ctx, opt):
     assert np.allclose(got_l, want_l, rtol=1e-5, atol=1e-6), (got_l, want_l)
     assert got_l[-1] < got_l[0]
     for k in want_p:
-        # four steps of f32 arithmetic in two summation orders: 1e-4 of the parameter scale
-        scale = float(np.abs(want_p[k]).max()) or 1.0
-        assert np.abs(got_p[k].astype(np.float64) - want_p[k].astype(np.float64)).max() <= 1e-4 * scale, k
+        # four steps of f32 arithmetic in two summation orders: 1e-4 of the parameter scale. Leaves whose
+        # gradient is zero in exact arithmetic (the key bias: softmax ignores a shift) hold pure rounding
+        # noise of the order lr * eps -- hence the absolute floor.
+        scale = float(np.abs(want_p[k]).max())
+        assert np.abs(got_p[k].astype(np.float64) - want_p[k].astype(np.float64)).max() <= 1e-4 * scale + 1e-7, k
 
 
 def test_bf16_sandwich_step_tracks_the_reference_backend(ctx):

@@ -200,7 +200,7 @@ def test_matmul_tc_tile_modes(ctx, oracle, dtype, pair_mode):
 
 
 def test_matmul_f32_large_runs_as_3xtf32_and_keeps_f32_accuracy(ctx, oracle):
-    """f32 products of >= 2 GFLOP take the tensor-core 3xTF32 path (nxc_matmul_x3.cu) by default.
+    """f32 products of >= 0.25 GFLOP take the tensor-core 3xTF32 path (nxc_matmul_x3.cu) by default.
     Against the reference binary's f32 result: 2e-5 of max (|A||B|) -- far inside the reference's own
     f32 tolerance (1e-3 rel + 1e-3 abs, backend_c/test/matmul_test.ml:831) and 50x tighter than plain
     tf32 gets; mode "ieee" pins the CUDA-core kernel and agrees to 2e-6. Transposed views, a K that
@@ -316,3 +316,27 @@ def test_matmul_m_major_lhs_with_wide_n_is_packed_and_bit_identical(ctx):
     got = H.bf16_bits_to_f32(via_view[:4]).astype(np.float64)
     bound = storage_ulp("bf16", want) + 2.0 * k * 2.0 ** -24 * (np.abs(xf[:, :4]).T @ np.abs(gf))
     assert (np.abs(got - want) <= bound).all(), float(np.max(np.abs(got - want) / bound))
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_matmul_broadcast_weight_batches_fold_into_rows(ctx, oracle, dtype):
+    """x [B, T, C] @ W [C, C'] (every Linear.apply of the GPT-2 step): the batches follow each other at
+    the row pitch, so the engine runs ONE product with B*T rows. Same answer as the reference's
+    batched loop; a batch that does NOT compose with the rows (a sliced batch) keeps the batched route."""
+    rng = np.random.default_rng(21)
+    Bt, T, C, C2 = 4, 64, 768, 768
+    X = H.to_storage(dtype, rng.standard_normal((Bt, T, C)) / 4)
+    W = H.to_storage(dtype, rng.standard_normal((C, C2)) / 16)
+    x = H.HostView(X.reshape(-1).copy(), dtype, [Bt, T, C])
+    w = H.HostView(W.reshape(-1).copy(), dtype, [C, C2])
+    x_sliced = H.HostView(np.tile(X.reshape(-1), 2), dtype, [2 * Bt, T, C]).shrink([(0, 2 * Bt), (0, T), (0, C)])
+    x_sliced = H.HostView(x_sliced.storage, dtype, [Bt, T, C], [2 * T * C, C, 1], 0)     # every other batch
+    for name, xv in (("dense", x), ("every other batch", x_sliced)):
+        want = oracle.matmul(xv, w).numpy()
+        got = H.download(B.matmul(H.upload(ctx, xv), H.upload(ctx, w)))
+        assert got.shape == (Bt, T, C2)
+        if dtype == "bf16":
+            assert_gemm_16bit(dtype, got, want, _absprod(dtype, xv, w), C, name)
+        else:
+            bound = float((np.abs(X.reshape(-1, C)).astype(np.float64) @ np.abs(W).astype(np.float64)).max())
+            assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 2e-5 * bound, name

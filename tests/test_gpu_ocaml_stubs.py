@@ -208,6 +208,8 @@ def test_full_transfer_errors_and_lifetime(sb, oracle):
     H.assert_close("c32", sb.download(sb.fft(sb.upload(z), [0])), oracle.fft(z, [0]).numpy(), rel=2e-6, abs_=2e-5, what="fft")
     # custom-block lifetime: dropping the wrappers runs the finalizer (nxc_free) and frees the block
     import gc
+    del got, x, b, out
+    gc.collect()                       # wrappers of the tensors above go first
     before = S.lib().nxstub_live()
     ts = [sb.create("f32", [1 << 20]) for _ in range(8)]
     assert S.lib().nxstub_live() == before + 8
