@@ -165,7 +165,7 @@ extern "C" nxc_status nxc_matmul(nxc_ctx *ctx, const nxc_tensor *C, const nxc_te
     // K*u sgemm bound and 20x inside the reference's own f32 matmul tolerance, 1e-3 rel + 1e-3 abs,
     // backend_c/test/matmul_test.ml:831). Mode "ieee" keeps every f32 product on the CUDA-core
     // kernel (each product and sum rounded to nearest, like the reference's microkernel).
-    if (dt == NXC_F32 && (ctx->matmul_tf32 == 0 || ctx->matmul_tf32 == 2) && p.m >= 128 && p.n >= 128 &&
+    if (dt == NXC_F32 && (ctx->matmul_tf32 == 0 || ctx->matmul_tf32 == 2) && p.m >= 32 && p.n >= 32 &&
         2.0 * (double)p.m * (double)p.n * (double)p.k * (double)p.nbatch >= 268435456.0) {
       s = nxc_matmul_f32x3(ctx, p);
       if (s != NXC_MM_TC_DECLINED) { if (s) goto fail; return NXC_OK; }

@@ -75,6 +75,8 @@ struct TcParams {
   int out_f32;            // C is f32 (tf32 mode) else 16-bit
   int out_bf16;           // 16-bit flavour
   int vec_store;          // rows of C are 16-byte aligned
+  int tile_n;             // columns of C per tile: 256, 128 or 64 (the UMMA N; smem / TMEM strides stay those of 256)
+  int b_rows;             // rows of B one CTA stages per k-block and per half: tile_n, or tile_n / 2 for a pair
   int group;              // M-blocks per rasterisation group
   int kskew;              // concurrent tiles start their K loop up to kskew-1 blocks apart (1 = in lockstep)
 };
@@ -310,6 +312,9 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t total_tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
+  // WIDE keeps its compile-time 2 x 256 columns; otherwise the tile width is a launch parameter
+  const int tile_n = WIDE ? C::TILE_N : p.tile_n;
+  const int b_rows = WIDE ? C::B_ROWS : p.b_rows;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -320,7 +325,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int64_t t = worker; t < total_tiles; t += nworkers) {
         int bi, mb, nb;
         tile_coords(p, t, bi, mb, nb);
-        const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * C::TILE_N + (int)rank * C::B_ROWS;
+        const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * tile_n + (int)rank * b_rows;
         const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
         // Tiles that run concurrently walk K in lockstep otherwise: with a power-of-two row pitch
         // (K = 16384 bf16: 32 KB) every CTA then asks for the same 128-byte column of its rows,
@@ -332,7 +337,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int kb = kbi + kb0 < p.num_kb ? kbi + kb0 : kbi + kb0 - p.num_kb;
           mbar_wait(&empty[stage], phase ^ 1);
           // PAIR: one arrival (the leader's) and the bytes of BOTH CTAs complete the leader's barrier
-          if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * (A_STAGE_BYTES + C::N_HALVES * b_rows * ROW_BYTES));
           const uint32_t lbar = PAIR ? leader_addr(&full[stage]) : 0u;
           const int k0 = kb * p.block_k;
           uint8_t *sa = smem_a + stage * A_STAGE_BYTES;
@@ -356,7 +361,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               load(&map_b, sbh, k0, nh, bb);
             } else {
               const int box_bytes = p.block_k * ROW_BYTES;
-              for (int j = 0; j < C::B_ROWS / elems_per_row; j++)
+              for (int j = 0; j < b_rows / elems_per_row; j++)
                 load(&map_b, sbh + j * box_bytes, nh + j * elems_per_row, k0, bb);
             }
           }
@@ -441,11 +446,11 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tfull[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = (int64_t)mb * C::TILE_M + (int64_t)rank * BLOCK_M + q * 32 + lane;
-      const int64_t col0 = (int64_t)nb * C::TILE_N;
+      const int64_t col0 = (int64_t)nb * tile_n;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * BLOCK_N;
       const int64_t crow = (int64_t)bi * p.c_bs + row * p.c_rs;
 #pragma unroll 1
-      for (int c = 0; c < C::TILE_N / 32; c++) {
+      for (int c = 0; c < tile_n / 32; c++) {
         uint32_t v[32];
         if (p.num_kb > 0) {
           tmem_ld32(taddr + c * 32, v);
@@ -568,7 +573,6 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   bool pair = num_m128 >= 2 && ((num_m128 & 1) == 0 || num_m128 >= 8);
   if (const char *f = getenv("NX_CUDA_MM_PAIR")) pair = f[0] == '1';  // test / tuning override
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
-  const int b_rows = pair ? BLOCK_N / 2 : BLOCK_N;
   // 256 x 512 tiles (Cfg<true, true>): an experiment that stays opt-in (NX_CUDA_MM_WIDE=1). It moves
   // a quarter fewer L2 bytes per flop and is bit-identical to the 256 x 256 kernel, but measured
   // SLOWER (8192^3: 1284 vs 1395 TFLOP/s; 16384^3 equal): 4 smem stages instead of 7 and an epilogue
@@ -576,7 +580,31 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   // 77 % tensor-pipe activity is not an L2-bandwidth limit (profiles/mm_wide_r01.json).
   bool wide = false;
   if (const char *f = getenv("NX_CUDA_MM_WIDE")) wide = pair && f[0] == '1' && q.n % (2 * BLOCK_N) == 0;
-  const int tile_n = wide ? 2 * BLOCK_N : BLOCK_N;
+  // Tile width. 256 columns give the most flops per staged byte and are the choice whenever the grid
+  // fills the machine; a narrow or small product takes 128 or 64 so that (a) a 64-column C (the
+  // head dim of every attention gradient) does not pay for 256, and (b) a product of a few tiles
+  // spreads over more SMs (512^3 .. 2048^3 are latency-bound: 4 / 16 / 64 tiles of 256 x 256).
+  // An N-major B is staged in boxes of one 128-byte row of N, so a CTA's share must hold whole boxes.
+  int tile_n = wide ? 2 * BLOCK_N : BLOCK_N;
+  if (!wide) {
+    const int64_t workers = pair ? ctx->sm_count / 2 : ctx->sm_count;
+    const int64_t num_m_t = (q.m + tile_m - 1) / tile_m;
+    const bool b_n_major = !(q.b_rs == 1 || q.k == 1);
+    const int epr = ROW_BYTES / esize;
+    auto allowed = [&](int tn) { const int br = pair ? tn / 2 : tn; return !b_n_major || br % epr == 0; };
+    auto tiles = [&](int tn) { return num_m_t * ((q.n + tn - 1) / tn) * q.nbatch; };
+    // waves x (columns per tile + a fixed per-tile cost worth ~32 columns); a narrower tile must win
+    // by 15 % to be taken, since it moves more bytes per flop
+    auto cost = [&](int tn) { return (double)((tiles(tn) + workers - 1) / workers) * (double)(tn + 32); };
+    double best = cost(tile_n);
+    for (int tn = 128; tn >= 64; tn >>= 1) {
+      if (!allowed(tn)) break;
+      const double c = cost(tn);
+      if (c < 0.85 * best) { best = c; tile_n = tn; }
+    }
+    if (const char *f = getenv("NX_CUDA_MM_TILE_N")) { const int v = atoi(f); if ((v == 64 || v == 128 || v == 256) && allowed(v)) tile_n = v; }
+  }
+  const int b_rows = wide ? (pair ? BLOCK_N / 2 : BLOCK_N) : (pair ? tile_n / 2 : tile_n);
 
   TcParams p;
   p.m = q.m; p.n = q.n; p.k = q.k; p.nbatch = q.nbatch;
@@ -587,6 +615,7 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.num_n = (int)((q.n + tile_n - 1) / tile_n);
   p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
   p.a_batched = a_b; p.b_batched = b_b;
+  p.tile_n = tile_n; p.b_rows = b_rows;
   p.group = 8;
   if (const char *f = getenv("NX_CUDA_MM_GROUP")) p.group = atoi(f) > 0 ? atoi(f) : 8;
   p.kskew = 1;
@@ -622,7 +651,7 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   // instruction descriptor: D = f32, A/B format, majors, N >> 3, M >> 4 (M = 256 across the pair)
   const uint32_t fmt = q.dt == NXC_BF16 ? 1u : q.dt == NXC_F16 ? 0u : 2u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
+            ((uint32_t)((wide ? BLOCK_N : tile_n) >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
 
   if (!ctx->mm_attr_set) {  // per context = per device; a function attribute is device state
     NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -50,6 +50,8 @@ def test_f32_step_matches_the_reference_backend(ctx, opt):
     assert np.allclose(got_l, want_l, rtol=1e-5, atol=1e-6), (got_l, want_l)
     assert got_l[-1] < got_l[0]
     for k in want_p:
+        if opt == "adamw" and k.endswith("attn.k.b"):
+            continue   # zero gradient in exact arithmetic: Adam normalises the rounding noise into full-size steps
         # four steps of f32 arithmetic in two summation orders: 1e-4 of the parameter scale. Leaves whose
         # gradient is zero in exact arithmetic (the key bias: softmax ignores a shift) hold pure rounding
         # noise of the order lr * eps -- hence the absolute floor.
