@@ -29,6 +29,7 @@ per step: 12N + 12N + 8N + 4N + 4N + 4N + 4N = 48 N bytes
            not available).
 `matmul`   bf16 8192^3 on the tcgen05 path, TFLOP/s against the measured bf16 peak (the second
            half of BASELINE.json's metric), with 64 rows of the product checked against float64.
+`sharded_batch_matmul`  a batch-leading bf16 matmul sharded on the batch axis, every rank its slab.
 `checks`   correctness asserted in this run: at N > 1 the sharded reductions against the closed
            form of the inputs, a planted maximum on the last rank and a NaN on rank 1 through
            the sharded argmax / max, bit-identity of the results across ranks; at every N the
@@ -524,6 +525,24 @@ def main():
         except Exception as e:  # report, never hide
             matmul = dict(matmul or {}, error=str(e))
 
+    # ---- batch-leading matmul sharded on the batch axis: every rank multiplies
+    # its own slab of the batch, no exchange; whole-job TFLOP/s, max over ranks -------------------
+    batch_mm = None
+    if not args.no_matmul:
+        try:
+            Bn, Mn = 8, 2048
+            xa = B.cast(B.reshape(B.shrink(a, [(0, Bn * Mn * Mn)]), [Bn, Mn, Mn]), D.bfloat16)
+            xb = B.cast(B.reshape(B.shrink(b, [(0, Bn * Mn * Mn)]), [Bn, Mn, Mn]), D.bfloat16)
+            sharded.sharded_batch_matmul(xa, xb, comm)
+            t_ms = timed(lambda: sharded.sharded_batch_matmul(xa, xb, comm), 10)
+            tf = world * 2.0 * Bn * Mn ** 3 / (t_ms * 1e-3) / 1e12
+            batch_mm = {"workload": f"bf16 [{Bn * world}, {Mn}, {Mn}] x [{Bn * world}, {Mn}, {Mn}], {Bn} batches per GPU",
+                        "ms": round(t_ms, 4), "value": round(tf, 1), "unit": "TFLOP/s",
+                        "frac_of_peak_per_gpu": round(tf / world / pk["bf16"], 4)}
+            del xa, xb
+        except Exception as e:
+            batch_mm = {"error": str(e)}
+
     # ---- end to end: host buffers in, host results out --------------------------------------
     # the clock sampler covers the device-timed regions above and stops here
     clocks = sampler.stop() if sampler else None
@@ -631,7 +650,7 @@ def main():
                            "parallelism": f"leading-axis slabs x{world}; each reduction = local kernel + one "
                                           f"exchange-and-fold kernel over NVLink peer memory" if dist else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "eager": eager, "checks": checks,
-                "roofline": roofline, "cpu_baseline": cpu, "matmul": matmul, "mlp_grad": mlp_grad, "gpt2_step": gpt2,
+                "roofline": roofline, "cpu_baseline": cpu, "matmul": matmul, "sharded_batch_matmul": batch_mm, "mlp_grad": mlp_grad, "gpt2_step": gpt2,
                 "impl": "cuda"}
         print(json.dumps(line))
     if comm is not None:

@@ -356,3 +356,20 @@ let eig x =
   let w = eig_values x and v = create_tensor x.context Dtype.Complex128 x.shape in
   lift_linalg ~op:"eig" (fun () -> caml_eig w v x true);
   (w, v)
+
+(* ---- step capture (beyond Backend_intf.S; see INTEGRATION.md section 2b). Between [capture_begin]
+   and [capture_end] every op issued on the context is recorded into a CUDA graph instead of running;
+   [graph_launch] replays the whole step with one launch. Tensors created inside the capture are the
+   replay's outputs and keep their addresses; tensors that existed before it are read in place. ---- *)
+type graph (* custom block around nxc_graph*, finalizer -> nxc_graph_destroy *)
+
+external capture_begin : context -> unit = "nx_cuda_capture_begin"
+external capture_end : context -> graph = "nx_cuda_capture_end"
+external graph_launch : context -> graph -> unit = "nx_cuda_graph_launch"
+external sync : context -> unit = "nx_cuda_sync"
+
+let capture ctx f =
+  capture_begin ctx;
+  match f () with
+  | v -> (v, capture_end ctx)
+  | exception e -> (try ignore (capture_end ctx) with _ -> ()); raise e

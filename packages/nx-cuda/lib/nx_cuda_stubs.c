@@ -363,3 +363,48 @@ CAMLprim value nx_cuda_eig(value vw, value vv, value vin, value vvectors) {
   if (s) raise_status("eig", CTX_OF(vw), s);
   CAMLreturn(Val_unit);
 }
+
+/* ---- step capture (nxc_capture_begin / _end / nxc_graph_launch; no reference counterpart: the
+   reference's answer to per-op overhead is Rune.jit, an eager device backend's is replay) ---- */
+typedef struct { nxc_graph *g; nxc_ctx *ctx; } graphbox;
+#define Graph_val(v) ((graphbox *)Data_custom_val(v))
+static void graph_finalize(value v) {
+  graphbox *b = Graph_val(v);
+  if (b->g) nxc_graph_destroy(b->ctx, b->g);
+}
+static struct custom_operations graph_ops = {"nx_cuda.graph", graph_finalize, custom_compare_default,
+    custom_hash_default, custom_serialize_default, custom_deserialize_default, custom_compare_ext_default,
+    custom_fixed_length_default};
+CAMLprim value nx_cuda_capture_begin(value vctx) {
+  CAMLparam1(vctx);
+  nxc_status s = nxc_capture_begin(Ctx_val(vctx));
+  if (s) raise_status("capture_begin", Ctx_val(vctx), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_capture_end(value vctx) {
+  CAMLparam1(vctx);
+  CAMLlocal1(v);
+  v = caml_alloc_custom(&graph_ops, sizeof(graphbox), 0, 1);
+  Graph_val(v)->g = NULL;
+  Graph_val(v)->ctx = Ctx_val(vctx);
+  nxc_graph *g = NULL;
+  nxc_status s = nxc_capture_end(Ctx_val(vctx), &g);
+  if (s) raise_status("capture_end", Ctx_val(vctx), s);
+  Graph_val(v)->g = g;
+  CAMLreturn(v);
+}
+CAMLprim value nx_cuda_graph_launch(value vctx, value vg) {
+  CAMLparam2(vctx, vg);
+  nxc_status s = nxc_graph_launch(Ctx_val(vctx), Graph_val(vg)->g);
+  if (s) raise_status("graph_launch", Ctx_val(vctx), s);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nx_cuda_sync(value vctx) {
+  CAMLparam1(vctx);
+  nxc_ctx *ctx = Ctx_val(vctx);
+  caml_enter_blocking_section();
+  nxc_status s = nxc_sync(ctx);
+  caml_leave_blocking_section();
+  if (s) raise_status("sync", ctx, s);
+  CAMLreturn(Val_unit);
+}

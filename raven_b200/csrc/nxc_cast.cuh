@@ -46,6 +46,12 @@ template <int SRC, int DST> struct KCast {
   __device__ __forceinline__ static float real_of(cf32 v) { return v.re; }
   __device__ __forceinline__ static double real_of(cf64 v) { return v.re; }
 
+  // float-class destinations: the conversion on compute-type values (see KUn::op)
+  static constexpr int OUT_DT = (B::cls == NXC_CLS_FLOAT) ? DST : -1, IN_DT = SRC;
+  __device__ __forceinline__ static CB op(CA a, CA, const P &) {
+    if constexpr (B::cls == NXC_CLS_FLOAT) return (CB)real_of(a);
+    else return CB();
+  }
   __device__ __forceinline__ static S0 run(S1 a, S2, S3, const P &) {
     CA v = A::ld(a);
     if constexpr (B::cls == NXC_CLS_FLOAT) {

@@ -284,6 +284,71 @@ NXC_DEF_DT(NXC_C64, cf64, cf64, NXC_CLS_COMPLEX, s, v)
 NXC_DEF_DT(NXC_BOOL, bool_s, uint32_t, NXC_CLS_BOOL, (uint32_t)(s.b != 0), (bool_s{(uint8_t)(v != 0)}))
 #undef NXC_DEF_DT
 
+// ---- packed stores of the 16-bit float types ------------------------------------------------------
+// N compute-type (float) results -> N storage values, two per hardware convert
+// (cvt.rn.{bf16x2,f16x2}.f32: one instruction per PAIR instead of ~9 integer operations per
+// element for the software round-to-nearest-even). The hardware turns every NaN into the
+// canonical 0x7FFF where the reference keeps sign and payload (nx_buffer_stubs.h:73-86, 99-148),
+// so one `setp.nan` per pair collects "was there a NaN at all" and a thread that saw one redoes
+// its whole vector with the exact scalar converters -- a branch that is never taken on real data.
+// Measured on B200 over all 2^32 float patterns (scratch/cvt_probe.cu): the hardware converts
+// agree with the reference's bit for bit on every non-NaN input.
+template <int DT> struct NxcPack16 { static constexpr bool v = (DT == NXC_F16 || DT == NXC_BF16); };
+template <int DT> __device__ __forceinline__ uint32_t nxc_cvt_pair16(float lo, float hi) {
+  uint32_t r;
+  if (DT == NXC_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t nxc_pair_has_nan(float a, float b) {
+  uint32_t r;
+  asm("{ .reg .pred q; setp.nan.f32 q, %1, %2; selp.u32 %0, 1, 0, q; }" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+template <int DT, int N>
+__device__ __forceinline__ void nxc_pack16(const float (&v)[N], typename DT_<DT>::S (&o)[N]) {
+  static_assert(N % 2 == 0, "pairs");
+  uint32_t w[N / 2], nan = 0;
+#pragma unroll
+  for (int j = 0; j < N / 2; j++) {
+    w[j] = nxc_cvt_pair16<DT>(v[2 * j], v[2 * j + 1]);
+    nan |= nxc_pair_has_nan(v[2 * j], v[2 * j + 1]);
+  }
+  if (nan) {
+#pragma unroll
+    for (int i = 0; i < N; i++) o[i] = DT_<DT>::st(v[i]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N / 2; j++) {
+      o[2 * j].b = (uint16_t)(w[j] & 0xFFFFu);
+      o[2 * j + 1].b = (uint16_t)(w[j] >> 16);
+    }
+  }
+}
+
+// N storage values -> N compute values. For f16 the hardware widening convert is exact on every
+// non-NaN pattern but canonicalises NaNs, where the reference quiets them and keeps the payload
+// (nx_buffer_stubs.h:150-182; measured: all 2046 NaN patterns differ, no other): convert
+// everything in hardware, test the RESULTS for NaN a pair at a time, and redo the vector with the
+// exact scalar converter only in a thread that met one. Every other dtype: N scalar loads.
+template <int DT, int N>
+__device__ __forceinline__ void nxc_ld_many(const typename DT_<DT>::S (&s)[N], typename DT_<DT>::C (&c)[N]) {
+  if constexpr (DT == NXC_F16 && N % 2 == 0) {
+    uint32_t nan = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) c[i] = __half2float(__ushort_as_half(s[i].b));
+#pragma unroll
+    for (int j = 0; j < N / 2; j++) nan |= nxc_pair_has_nan(c[2 * j], c[2 * j + 1]);
+    if (nan) {
+#pragma unroll
+      for (int i = 0; i < N; i++) c[i] = nxc_half_to_float(s[i].b);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) c[i] = DT_<DT>::ld(s[i]);
+  }
+}
+
 // Dispatch a runtime dtype tag to a template instantiation over the 17 compute
 // dtypes. BODY sees `DT` as a constexpr int.
 #define NXC_DISPATCH_DTYPE(dt, ...)                                             \

@@ -39,6 +39,16 @@ template <int OP, int DT> struct RedP {
     }
   }
   __device__ __forceinline__ static void step(A &acc, S s, int64_t) { acc = combine(acc, D::ld(s)); }
+  // f16: a vector's worth of elements is widened in bulk (nxc_ld_many: hardware converts, NaN
+  // patterns redone exactly) -- the per-element software NaN test held f16 row sums at half the HBM rate
+  static constexpr bool MANY = (DT == NXC_F16);
+  template <int N>
+  __device__ __forceinline__ static void step_many(A &acc, const S (&vals)[N], int64_t, int64_t) {
+    typename D::C c[N];
+    nxc_ld_many<DT, N>(vals, c);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc = combine(acc, c[i]);
+  }
   __device__ __forceinline__ static A combine(A a, A b) {
     if constexpr (cls == NXC_CLS_COMPLEX) {
       return OP == NXC_SUM ? zadd(a, b) : zmul(a, b);

@@ -133,11 +133,46 @@ template <class K> struct NxcKInfo {
   static constexpr int IPT_RAW = 16 / min_size;
   static constexpr int IPT = IPT_RAW * max_size > 64 ? 64 / max_size : IPT_RAW;
   // independent steps in flight: aim at 64 bytes of the largest type per thread
-  static constexpr int UNROLL_RAW = 64 / (IPT * max_size);
+  // ... and at least 32 bytes of the SMALLEST: a widening cast (i8 -> f32: one 16-byte load feeding
+  // four 16-byte stores) otherwise keeps a single load in flight per thread (measured 0.70)
+  static constexpr int UNROLL_BIG = 64 / (IPT * max_size), UNROLL_SMALL = 32 / (IPT * min_size);
+  static constexpr int UNROLL_RAW = UNROLL_BIG > UNROLL_SMALL ? UNROLL_BIG : UNROLL_SMALL;
   static constexpr int UNROLL = UNROLL_RAW < 1 ? 1 : (UNROLL_RAW > 4 ? 4 : UNROLL_RAW);
 };
 
 #define NXC_MAP_THREADS 256
+
+// N results of one op. Ops that declare IN_DT / OUT_DT / op() (unary, binary, casts to a float type)
+// and touch a 16-bit float type convert in bulk: f16 inputs through nxc_ld_many, f16 / bf16 results
+// through nxc_pack16 (two per hardware convert); everything else is N scalar calls.
+template <class K, class = void> struct NxcBulk { static constexpr bool v = false; };
+template <class K> struct NxcBulk<K, typename std::enable_if<(K::OUT_DT >= 0)>::type> {
+  static constexpr bool v = K::OUT_DT == NXC_F16 || K::OUT_DT == NXC_BF16 || K::IN_DT == NXC_F16;
+};
+template <class K, int N>
+__device__ __forceinline__ void nxc_run_vec(const typename K::S1 (&a)[N], const typename K::S2 (&b)[N],
+                                            const typename K::S3 (&c)[N], typename K::S0 (&o)[N], const typename K::P &prm) {
+  if constexpr (N % 2 == 0 && NxcBulk<K>::v) {
+    constexpr int IDT = K::IN_DT, ODT = K::OUT_DT;
+    typedef typename DT_<IDT>::C CI;
+    typedef typename DT_<ODT>::C CO;
+    CI ca[N], cb[N];
+    nxc_ld_many<IDT, N>(a, ca);
+    if constexpr (K::NIN >= 2) nxc_ld_many<IDT, N>(b, cb);
+    CO v[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = K::op(ca[i], K::NIN >= 2 ? cb[i] : ca[i], prm);
+    if constexpr (ODT == NXC_F16 || ODT == NXC_BF16) {
+      nxc_pack16<ODT, N>(v, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++) o[i] = DT_<ODT>::st(v[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i++) o[i] = K::run(a[i], b[i], c[i], prm);
+  }
+}
 
 // ---- flat kernel -------------------------------------------------------------------
 template <class K>
@@ -175,8 +210,7 @@ nxc_map_flat_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__re
     for (int u = 0; u < UNROLL; u++) {
       const int64_t e = tile0 + ((int64_t)u * NXC_MAP_THREADS + threadIdx.x) * IPT;
       S0 vo[IPT];
-#pragma unroll
-      for (int i = 0; i < IPT; i++) vo[i] = K::run(va[u][i], vb[u][i], vc[u][i], prm);
+      nxc_run_vec<K, IPT>(va[u], vb[u], vc[u], vo, prm);
       nxc_store_vec<S0, IPT>(out + e, vo);
     }
   } else {
@@ -330,10 +364,14 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
       for (int u = 0; u < U; u++) {
         if (u < n_live) {
           S0 vo[VW];
+          S1 ea[VW]; S2 eb[VW]; S3 ec[VW];
 #pragma unroll
-          for (int i = 0; i < VW; i++)
-            vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, cba, na_), nxc_item_elem<S2, VW>(vb[u], xb[u], i, cbb, nb_),
-                           nxc_item_elem<S3, VW>(vc[u], xc[u], i, cbc, nc_), prm);
+          for (int i = 0; i < VW; i++) {
+            ea[i] = nxc_item_elem<S1, VW>(va[u], xa[u], i, cba, na_);
+            eb[i] = nxc_item_elem<S2, VW>(vb[u], xb[u], i, cbb, nb_);
+            ec[i] = nxc_item_elem<S3, VW>(vc[u], xc[u], i, cbc, nc_);
+          }
+          nxc_run_vec<K, VW>(ea, eb, ec, vo, prm);
           if (VW == 1) po[0] = vo[0];
           else nxc_store_vec<S0, VW>(po, vo);
         }
@@ -361,10 +399,14 @@ nxc_map_strided_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *_
       for (int u = 0; u < U; u++) {
         if (u < n_live) {
           S0 vo[VW];
+          S1 ea[VW]; S2 eb[VW]; S3 ec[VW];
 #pragma unroll
-          for (int i = 0; i < VW; i++)
-            vo[i] = K::run(nxc_item_elem<S1, VW>(va[u], xa[u], i, ba, na), nxc_item_elem<S2, VW>(vb[u], xb[u], i, bb, nb),
-                           nxc_item_elem<S3, VW>(vc[u], xc[u], i, bc, nc), prm);
+          for (int i = 0; i < VW; i++) {
+            ea[i] = nxc_item_elem<S1, VW>(va[u], xa[u], i, ba, na);
+            eb[i] = nxc_item_elem<S2, VW>(vb[u], xb[u], i, bb, nb);
+            ec[i] = nxc_item_elem<S3, VW>(vc[u], xc[u], i, bc, nc);
+          }
+          nxc_run_vec<K, VW>(ea, eb, ec, vo, prm);
           if (VW == 1) po[0] = vo[0];
           else nxc_store_vec<S0, VW>(po, vo);
         }
@@ -562,13 +604,14 @@ nxc_map_tiledv_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__
     const uint32_t jl = ry + RP * r, gj = j0 + jl, gi = i0 + vx * V;
     if (gi < g.SI && gj < g.SJ) {
       S0 vo[V];
+      S1 ea[V]; S2 eb[V]; S3 ec[V];
 #pragma unroll
       for (int q = 0; q < V; q++) {
-        S1 xa = S1(); S2 xb = S2();
-        if (K::NIN >= 1) xa = a_t ? ta[K::NIN >= 1 ? vx * V + q : 0][jl] : ra[r][q];
-        if (K::NIN >= 2) xb = b_t ? tb[K::NIN >= 2 ? vx * V + q : 0][jl] : rb[r][q];
-        vo[q] = K::run(xa, xb, S3(), prm);
+        ea[q] = S1(); eb[q] = S2(); ec[q] = S3();
+        if (K::NIN >= 1) ea[q] = a_t ? ta[K::NIN >= 1 ? vx * V + q : 0][jl] : ra[r][q];
+        if (K::NIN >= 2) eb[q] = b_t ? tb[K::NIN >= 2 ? vx * V + q : 0][jl] : rb[r][q];
       }
+      nxc_run_vec<K, V>(ea, eb, ec, vo, prm);
       nxc_store_vec<S0, V>(out + base[0] + (int64_t)gj * g.sj[0] + gi, vo);
     }
   }

@@ -327,6 +327,10 @@ template <int OP, int DT> struct KUn {
   static constexpr int NIN = 1;
   typedef typename D::S S0; typedef typename D::S S1; typedef typename D::S S2; typedef typename D::S S3;
   typedef NxcNoP P;
+  // the op on compute-type values: the vector paths convert f16 inputs and f16 / bf16 results in bulk
+  // (nxc_ld_many, nxc_pack16) around it
+  static constexpr int OUT_DT = DT, IN_DT = DT;
+  __device__ __forceinline__ static typename D::C op(typename D::C a, typename D::C, const P &) { return O::f(a); }
   __device__ __forceinline__ static S0 run(S1 a, S2, S3, const P &) { return D::st(O::f(D::ld(a))); }
 };
 template <int OP, int DT> struct KBin {
@@ -338,6 +342,8 @@ template <int OP, int DT> struct KBin {
   static constexpr int NIN = 2;
   typedef typename D::S S0; typedef typename D::S S1; typedef typename D::S S2; typedef typename D::S S3;
   typedef NxcNoP P;
+  static constexpr int OUT_DT = DT, IN_DT = DT;
+  __device__ __forceinline__ static typename D::C op(typename D::C a, typename D::C b, const P &) { return O::f(a, b); }
   __device__ __forceinline__ static S0 run(S1 a, S2 b, S3, const P &) { return D::st(O::f(D::ld(a), D::ld(b))); }
 };
 template <int OP, int DT> struct KCmp {

@@ -310,3 +310,16 @@ class StubBackend:
         out = self.create(x.dtype, x.shape)
         self._call("nx_cuda_fft", 4, lambda a: [val_int(1 if inverse else 0), out.record(a), x.record(a), a.ints(axes)])
         return out
+
+    # ---- step capture ----
+    def capture_begin(self):
+        invoke("nx_cuda_capture_begin", 1, [self.ctx.value])
+
+    def capture_end(self):
+        return Custom(invoke("nx_cuda_capture_end", 1, [self.ctx.value]))
+
+    def graph_launch(self, g):
+        invoke("nx_cuda_graph_launch", 2, [self.ctx.value, g.value])
+
+    def sync(self):
+        invoke("nx_cuda_sync", 1, [self.ctx.value])

@@ -217,3 +217,33 @@ def test_full_transfer_errors_and_lifetime(sb, oracle):
     del ts
     gc.collect()
     assert S.lib().nxstub_live() == before
+
+
+def test_capture_stubs_replay_a_step(sb, oracle):
+    """nx_cuda_capture_begin / _end / nx_cuda_graph_launch: ops issued through the stubs between begin
+    and end are recorded, the graph value is a custom block (finalizer -> nxc_graph_destroy), a replay
+    rewrites the outputs in place, and a blocking call inside a capture raises Failure."""
+    rng = np.random.default_rng(8)
+    a = H.HostView(rng.uniform(-2, 2, 4096).astype(np.float32), "f32", [64, 64])
+    b = H.HostView(rng.uniform(-2, 2, 4096).astype(np.float32), "f32", [64, 64])
+    ta, tb = sb.upload(a), sb.upload(b)
+    sb.capture_begin()
+    r = sb.binary("mul", sb.binary("add", ta, tb), sb.permute(ta, [1, 0]))
+    s = sb.reduce("sum", r, [1])
+    g = sb.capture_end()
+    assert S.lib().nxstub_custom_identifier(g.value) == b"nx_cuda.graph"
+    sb.graph_launch(g)
+    want_r = oracle.binary("mul", oracle.binary("add", a, b), a.permute([1, 0]))
+    H.assert_same("f32", sb.download(r), want_r.numpy(), ulp=0, what="captured mul(add)")
+    H.assert_close("f32", sb.download(s), oracle.reduce("sum", want_r, [1]).numpy(), rel=1e-5, abs_=1e-5, what="captured sum")
+    # refreshed input, in place; the replay sees it
+    a2 = H.HostView(rng.uniform(-2, 2, 4096).astype(np.float32), "f32", [64, 64])
+    sb.assign(ta, sb.upload(a2))
+    sb.graph_launch(g)
+    want_r = oracle.binary("mul", oracle.binary("add", a2, b), a2.permute([1, 0]))
+    H.assert_same("f32", sb.download(r), want_r.numpy(), ulp=0, what="replay over a refreshed input")
+    sb.capture_begin()
+    with pytest.raises(Failure, match="^to_host: operation not allowed while a step is being captured"):
+        sb.to_host(ta)
+    sb.capture_end()
+    sb.sync()
