@@ -629,6 +629,10 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   // plenty of rows: keep a row inside one warp (shuffle-only combine, no block barrier) and let
   // each lane walk the row; many threads per row only pay off when rows are scarce
   if (tl > 5 && items <= 512 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
+  // 1- and 2-byte elements: a 16 K-element row is only 16-32 KB, so a block per row spends as long in
+  // its barrier-and-shuffle epilogue as in its loads (bf16 / i8 inner-axis sums of [16384, 16384]:
+  // 0.75 / 0.49 of the HBM rate). With rows to spare a warp walks the whole row instead.
+  if (tl > 5 && sizeof(S) <= 2 && items <= 2048 && p.nr <= 1 && p.nk <= 1 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   // ... and with rows to spare, fewer lanes per row, 8 work items each: the per-row epilogue (a
   // shuffle butterfly, for argreduce also the index vote) is paid per thread GROUP, and at 32 lanes
   // per 256-element row it was a quarter of the argmax kernel's instructions. Not below 8 lanes:

@@ -41,13 +41,27 @@ template <int OP, int DT> struct RedP {
   __device__ __forceinline__ static void step(A &acc, S s, int64_t) { acc = combine(acc, D::ld(s)); }
   // f16: a vector's worth of elements is widened in bulk (nxc_ld_many: hardware converts, NaN
   // patterns redone exactly) -- the per-element software NaN test held f16 row sums at half the HBM rate
-  static constexpr bool MANY = (DT == NXC_F16);
+  // 8-bit integer sums: four elements per DP4A against a vector of ones (the accumulator is the
+  // 32-bit compute type; sums wrap modulo 2^32 and are truncated on store, as the reference's wider
+  // accumulator is -- nx_c.h:109-116)
+  static constexpr bool BYTE_SUM = OP == NXC_SUM && (DT == NXC_I8 || DT == NXC_U8);
+  static constexpr bool MANY = (DT == NXC_F16) || BYTE_SUM;
   template <int N>
   __device__ __forceinline__ static void step_many(A &acc, const S (&vals)[N], int64_t, int64_t) {
-    typename D::C c[N];
-    nxc_ld_many<DT, N>(vals, c);
+    if constexpr (BYTE_SUM && N % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i++) acc = combine(acc, c[i]);
+      for (int j = 0; j < N / 4; j++) {
+        const uint32_t w = (uint32_t)(uint8_t)vals[4 * j] | ((uint32_t)(uint8_t)vals[4 * j + 1] << 8) |
+                           ((uint32_t)(uint8_t)vals[4 * j + 2] << 16) | ((uint32_t)(uint8_t)vals[4 * j + 3] << 24);
+        if constexpr (DT == NXC_I8) acc = (A)__dp4a((int)w, (int)0x01010101, (int)acc);
+        else acc = (A)__dp4a(w, 0x01010101u, (unsigned)acc);
+      }
+    } else {
+      typename D::C c[N];
+      nxc_ld_many<DT, N>(vals, c);
+#pragma unroll
+      for (int i = 0; i < N; i++) acc = combine(acc, c[i]);
+    }
   }
   __device__ __forceinline__ static A combine(A a, A b) {
     if constexpr (cls == NXC_CLS_COMPLEX) {
