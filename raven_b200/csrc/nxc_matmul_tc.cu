@@ -167,10 +167,20 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // shared::cluster address of `p`'s counterpart in the even (leader) CTA of the pair
-__device__ __forceinline__ uint32_t leader_addr(const void *p) {
+__device__ __forceinline__ uint32_t leader_addr(const void *p, uint32_t leader_rank = 0) {
   uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(leader_rank));
   return r;
+}
+// one TMA box delivered to the same CTA-relative offset of every CTA in `mask`; each destination's
+// OWN barrier (same offset) receives the bytes
+__device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "h"(mask)
+      : "memory");
 }
 // both CTAs of the pair load their own slice; the bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap *map, uint32_t leader_bar, void *dst, int c0, int c1,
@@ -200,11 +210,11 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
       : "memory");
 }
 // arrives on the barrier at this offset in BOTH CTAs once the pair's MMAs issued so far retire
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
@@ -263,7 +273,22 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int64_t t, int &b
   nb = rr / gsz;
 }
 
-template <bool PAIR, bool WIDE>
+// QUAD (PAIR only): a cluster of FOUR CTAs = two pairs working on the tiles (mb, nb) and (mb + 1, nb).
+// They need the same B tile, and the pair kernel is bound by operand delivery (halving the tile
+// width, +50 % bytes per flop, costs 30 %: profiles/mm_knobs_r02.json), so B is fetched ONCE for
+// both: every CTA issues one quarter of the 256-column B slab as a TMA multicast to itself and to
+// its sibling in the other pair (ranks r and r ^ 2), plus its own 128 rows of A -- 24 KB of L2
+// reads per CTA and k-block instead of 32. Barrier protocol:
+//   full[s]   per CTA, one arrival (its own expect_tx) + 32 KB: 16 KB A, 8 KB B issued by itself,
+//             8 KB B issued by the sibling. Plain (cta_group::1) TMA semantics: the bytes count on
+//             the barrier of the CTA they land in.
+//   pfull[s]  on each pair leader: the odd CTA's otherwise idle warp 1 waits for ITS full[s] and
+//             forwards one arrival, so the leader issues the pair's MMAs once both halves are in.
+//   empty[s]  per CTA, TWO arrivals: the tcgen05.commit of BOTH leaders, multicast to all four CTAs
+//             -- a producer's multicast writes into the other pair's shared memory, so a slot is
+//             free only when both pairs' MMAs that read it have retired.
+// TMEM, the epilogue and the pair-internal tfull / tempty handshake are those of PAIR.
+template <bool PAIR, bool WIDE, bool QUAD = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  void *__restrict__ Cout, const __grid_constant__ TcParams p) {
@@ -276,18 +301,22 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t *smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+  uint64_t *pfull = bars + 2 * STAGES + 4;  // QUAD only
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
-  const int64_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
-  const int64_t nworkers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // rank in the cluster: 0-1 (PAIR) or 0-3 (QUAD)
+  const uint32_t rank = crank & 1u;                        // role in the pair: 0 = leader (issues the MMAs)
+  const uint32_t pairid = QUAD ? (crank >> 1) : 0u;        // which of the cluster's two pairs
+  const uint32_t lrank = crank & ~1u;                      // cluster rank of this CTA's pair leader
+  const int64_t worker = QUAD ? (blockIdx.x >> 2) : PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int64_t nworkers = QUAD ? (gridDim.x >> 2) : PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], QUAD ? 2 : 1); mbar_init(&pfull[s], 1); }
     // tempty is only waited on by the leader's MMA warp: 4 epilogue warps of each CTA arrive on it
     for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -311,6 +340,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  // QUAD: the work unit is two M-blocks of one N-block; p.num_m then counts UNITS (the host halves it)
   const int64_t total_tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
   // WIDE keeps its compile-time 2 x 256 columns; otherwise the tile width is a launch parameter
   const int tile_n = WIDE ? C::TILE_N : p.tile_n;
@@ -325,6 +355,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int64_t t = worker; t < total_tiles; t += nworkers) {
         int bi, mb, nb;
         tile_coords(p, t, bi, mb, nb);
+        if (QUAD) mb = 2 * mb + (int)pairid;
         const int m0 = mb * C::TILE_M + (int)rank * BLOCK_M, n0 = nb * tile_n + (int)rank * b_rows;
         const int ba = p.a_batched ? bi : 0, bb = p.b_batched ? bi : 0;
         // Tiles that run concurrently walk K in lockstep otherwise: with a power-of-two row pitch
@@ -336,14 +367,16 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kbi = 0; kbi < p.num_kb; kbi++) {
           const int kb = kbi + kb0 < p.num_kb ? kbi + kb0 : kbi + kb0 - p.num_kb;
           mbar_wait(&empty[stage], phase ^ 1);
-          // PAIR: one arrival (the leader's) and the bytes of BOTH CTAs complete the leader's barrier
-          if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * (A_STAGE_BYTES + C::N_HALVES * b_rows * ROW_BYTES));
-          const uint32_t lbar = PAIR ? leader_addr(&full[stage]) : 0u;
+          // PAIR: one arrival (the leader's) and the bytes of BOTH CTAs complete the leader's barrier.
+          // QUAD: every CTA counts the bytes that land in ITS shared memory on its own barrier.
+          if (QUAD) mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_rows * ROW_BYTES);
+          else if (rank == 0) mbar_expect_tx(&full[stage], (PAIR ? 2 : 1) * (A_STAGE_BYTES + C::N_HALVES * b_rows * ROW_BYTES));
+          const uint32_t lbar = (PAIR && !QUAD) ? leader_addr(&full[stage]) : 0u;
           const int k0 = kb * p.block_k;
           uint8_t *sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t *sb = smem_b + stage * B_STAGE_BYTES;
           auto load = [&](const CUtensorMap *map, void *dst, int c0, int c1, int c2) {
-            if (PAIR) tma_load_3d_pair(map, lbar, dst, c0, c1, c2);
+            if (PAIR && !QUAD) tma_load_3d_pair(map, lbar, dst, c0, c1, c2);
             else tma_load_3d(map, &full[stage], dst, c0, c1, c2);
           };
           if (!p.a_mn) {
@@ -353,6 +386,21 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = 0; j < BLOCK_M / elems_per_row; j++)
               load(&map_a, sa + j * box_bytes, m0 + j * elems_per_row, k0, ba);
           }
+          if (QUAD) {
+            // my quarter of the B slab: half of this CTA's b_rows rows, delivered to this CTA and to
+            // its sibling in the other pair (cluster ranks rank and rank + 2)
+            const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+            const int half = b_rows / 2;
+            if (!p.b_mn) {
+              tma_load_3d_mcast(&map_b, &full[stage], sb + pairid * half * ROW_BYTES, k0, n0 + (int)pairid * half, bb, mask);
+            } else {
+              const int box_bytes = p.block_k * ROW_BYTES, boxes = half / elems_per_row;
+              for (int j = 0; j < boxes; j++) {
+                const int jj = (int)pairid * boxes + j;
+                tma_load_3d_mcast(&map_b, &full[stage], sb + jj * box_bytes, n0 + jj * elems_per_row, k0, bb, mask);
+              }
+            }
+          } else
 #pragma unroll
           for (int h = 0; h < C::N_HALVES; h++) {  // WIDE: this CTA's 128 columns of each 256-column half
             uint8_t *sbh = sb + h * C::B_HALF_BYTES;
@@ -368,6 +416,18 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+    }
+  } else if (QUAD && warp == 1 && rank == 1) {
+    // ===== QUAD, odd CTA: forward "my half of the stage has landed" to the pair leader =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = worker; t < total_tiles; t += nworkers)
+        for (int kb = 0; kb < p.num_kb; kb++) {
+          mbar_wait(&full[stage], phase);
+          mbar_arrive_cluster(leader_addr(&pfull[stage], lrank));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
     }
   } else if (warp == 1 && rank == 0) {
     // ===== MMA issuer (the leader CTA only when PAIR) =====
@@ -394,6 +454,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t tmem_d = tmem_base + (uint32_t)as * BLOCK_N;  // WIDE: as == 0, both halves side by side
       for (int kb = 0; kb < p.num_kb; kb++) {
         mbar_wait(&full[stage], phase);
+        if (QUAD) mbar_wait_cluster(&pfull[stage], phase);  // the odd CTA's half
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
@@ -418,9 +479,9 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         __syncwarp();
         if (elect_one()) {
-          if (PAIR) {  // both CTAs' producers / epilogues are released
-            umma_commit_pair(&empty[stage]);
-            if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as]);
+          if (PAIR) {  // both CTAs' producers / epilogues are released (QUAD: the producers of all four)
+            umma_commit_pair(&empty[stage], QUAD ? (uint16_t)15 : (uint16_t)3);
+            if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as], (uint16_t)(3u << lrank));
           } else {
             umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
             if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
@@ -430,7 +491,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (p.num_kb == 0) {  // k == 0: nothing accumulates; the epilogue writes zeros
-        if (elect_one()) { if (PAIR) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]); }
+        if (elect_one()) { if (PAIR) umma_commit_pair(&tfull[as], (uint16_t)(3u << lrank)); else umma_commit(&tfull[as]); }
         __syncwarp();
       }
       if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
@@ -443,6 +504,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int64_t t = worker; t < total_tiles; t += nworkers) {
       int bi, mb, nb;
       tile_coords(p, t, bi, mb, nb);
+      if (QUAD) mb = 2 * mb + (int)pairid;
       mbar_wait(&tfull[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = (int64_t)mb * C::TILE_M + (int64_t)rank * BLOCK_M + q * 32 + lane;
@@ -494,7 +556,7 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(leader_addr(&tempty[as]));
+        if (PAIR) mbar_arrive_cluster(leader_addr(&tempty[as], lrank));
         else mbar_arrive(&tempty[as]);
       }
       if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
@@ -605,6 +667,16 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
     if (const char *f = getenv("NX_CUDA_MM_TILE_N")) { const int v = atoi(f); if ((v == 64 || v == 128 || v == 256) && allowed(v)) tile_n = v; }
   }
   const int b_rows = wide ? (pair ? BLOCK_N / 2 : BLOCK_N) : (pair ? tile_n / 2 : tile_n);
+  // Four-CTA clusters sharing B by multicast (see the kernel): products that fill the machine with
+  // full-width tiles -- that is where operand delivery binds. Opt-in until measured
+  // (NX_CUDA_MM_QUAD=1), off for anything else.
+  bool quad = false;
+  if (const char *f = getenv("NX_CUDA_MM_QUAD")) {
+    const int epr_b = ROW_BYTES / esize;
+    const bool b_n_major_q = !(q.b_rs == 1 || q.k == 1);
+    quad = f[0] == '1' && pair && !wide && tile_n == BLOCK_N && q.m > 2 * BLOCK_M &&
+           (!b_n_major_q || (b_rows / 2) % epr_b == 0);
+  }
 
   TcParams p;
   p.m = q.m; p.n = q.n; p.k = q.k; p.nbatch = q.nbatch;
@@ -612,6 +684,7 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.esize = esize;
   p.block_k = ROW_BYTES / esize;
   p.num_m = (int)((q.m + tile_m - 1) / tile_m);
+  if (quad) p.num_m = (p.num_m + 1) / 2;   // units of two M-blocks (an odd tail computes one block out of range)
   p.num_n = (int)((q.n + tile_n - 1) / tile_n);
   p.num_kb = (int)((q.k + p.block_k - 1) / p.block_k);
   p.a_batched = a_b; p.b_batched = b_b;
@@ -644,7 +717,7 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   if (!p.a_mn) ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.k, q.m, q.a_rs, a_b ? q.nbatch : 1, a_bs, BLOCK_M);
   else ok = encode_operand(ctx, &map_a, q.a, tdt, esize, q.m, q.k, q.a_cs, a_b ? q.nbatch : 1, a_bs, p.block_k, esize == 4);
   if (!ok) return NXC_MM_TC_DECLINED;
-  if (!p.b_mn) ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.k, q.n, q.b_cs, b_b ? q.nbatch : 1, b_bs, b_rows);
+  if (!p.b_mn) ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.k, q.n, q.b_cs, b_b ? q.nbatch : 1, b_bs, quad ? b_rows / 2 : b_rows);
   else ok = encode_operand(ctx, &map_b, q.b, tdt, esize, q.n, q.k, q.b_rs, b_b ? q.nbatch : 1, b_bs, p.block_k, esize == 4);
   if (!ok) return NXC_MM_TC_DECLINED;
 
@@ -660,12 +733,42 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
                                            Cfg<true>::SMEM_BYTES));
     NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true, true>::SMEM_BYTES));
+    NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_mm_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true>::SMEM_BYTES));
     ctx->mm_attr_set = 1;
   }
   const int64_t tiles = (int64_t)p.num_m * p.num_n * p.nbatch;
   if (!pair) {
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     nxc_mm_tc_kernel<false, false><<<grid, NUM_THREADS, Cfg<false>::SMEM_BYTES, ctx->stream>>>(map_a, map_b, (void *)q.c, p);
+  } else if (quad) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<true>::SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    static int quad_clusters = 0;       // one device per process (one process per GPU)
+    if (quad_clusters == 0) {   // how many 4-CTA clusters of this kernel the device runs at once
+      int nc = 0;
+      cfg.gridDim = dim3((unsigned)(4 * (ctx->sm_count / 4)));
+      if (cudaOccupancyMaxActiveClusters(&nc, nxc_mm_tc_kernel<true, false, true>, &cfg) != cudaSuccess || nc < 1) {
+        cudaGetLastError();
+        nc = ctx->sm_count / 4 - 2;
+      }
+      quad_clusters = nc;
+    }
+    const int64_t clusters = quad_clusters;
+    cfg.gridDim = dim3((unsigned)(4 * (tiles < clusters ? tiles : clusters)));
+    void *out = (void *)q.c;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, nxc_mm_tc_kernel<true, false, true>, map_a, map_b, out, p);
+    if (e != cudaSuccess) return nxc_cuda_fail(ctx, e, "cluster launch (4 CTAs)");
   } else {
     const int64_t pairs = ctx->sm_count / 2;
     cudaLaunchConfig_t cfg;
