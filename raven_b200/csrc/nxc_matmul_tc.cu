@@ -79,6 +79,7 @@ struct TcParams {
   int b_rows;             // rows of B one CTA stages per k-block and per half: tile_n, or tile_n / 2 for a pair
   int group;              // M-blocks per rasterisation group
   int kskew;              // concurrent tiles start their K loop up to kskew-1 blocks apart (1 = in lockstep)
+  int prefetch;           // k-blocks ahead of the staged one whose boxes are prefetched into L2 (0 = none)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +110,11 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// the same box, fetched into L2 only (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -413,6 +419,22 @@ nxc_mm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 load(&map_b, sbh + j * box_bytes, nh + j * elems_per_row, k0, bb);
             }
           }
+          // A stage is usable only when ALL its boxes have landed, and with a 78 % L2 hit rate most
+          // stages contain at least one box that comes from DRAM: ask L2 for the boxes of a later
+          // k-block now, so that the staging loads hit.
+          if (p.prefetch > 0 && kbi + p.prefetch < p.num_kb) {
+            const int kbp = kbi + p.prefetch + kb0 < p.num_kb ? kbi + p.prefetch + kb0 : kbi + p.prefetch + kb0 - p.num_kb;
+            const int kp0 = kbp * p.block_k;
+            if (!p.a_mn) tma_prefetch_3d(&map_a, kp0, m0, ba);
+            else for (int j = 0; j < BLOCK_M / elems_per_row; j++) tma_prefetch_3d(&map_a, m0 + j * elems_per_row, kp0, ba);
+            if (!QUAD) {
+              for (int h = 0; h < C::N_HALVES; h++) {
+                const int nh = n0 + h * BLOCK_N;
+                if (!p.b_mn) tma_prefetch_3d(&map_b, kp0, nh, bb);
+                else for (int j = 0; j < b_rows / elems_per_row; j++) tma_prefetch_3d(&map_b, nh + j * elems_per_row, kp0, bb);
+              }
+            }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -694,6 +716,8 @@ nxc_status nxc_matmul_tc(nxc_ctx *ctx, const NxcMatmulProblem &q) {
   p.kskew = 1;
   if (const char *f = getenv("NX_CUDA_MM_KSKEW")) p.kskew = atoi(f) > 0 ? atoi(f) : 1;
   if (p.kskew > p.num_kb) p.kskew = p.num_kb > 0 ? p.num_kb : 1;
+  p.prefetch = 0;
+  if (const char *f = getenv("NX_CUDA_MM_PREFETCH")) p.prefetch = atoi(f) > 0 ? atoi(f) : 0;
   p.out_f32 = (q.dt == NXC_F32);
   p.out_bf16 = (q.dt == NXC_BF16);
   p.vec_store = (((uintptr_t)q.c & 15) == 0) && ((q.c_rs * esize) % 16 == 0) && ((c_bs * esize) % 16 == 0);

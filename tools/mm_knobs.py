@@ -16,15 +16,17 @@ stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx = B.create_context(device=0, stream=stream.cuda_stream)
 out = {}
-for n in (4096, 8192):
+for n in (2048, 4096, 8192, 16384):
     rng = np.random.default_rng(n)
     a = B.cast(B.reshape(B.from_host(ctx, rng.standard_normal(n * n).astype(np.float32)), [n, n]), "bf16")
     b = B.cast(B.reshape(B.from_host(ctx, rng.standard_normal(n * n).astype(np.float32)), [n, n]), "bf16")
     for name, env in (("default", {}), ("tile_n=128", {"NX_CUDA_MM_TILE_N": "128"}), ("tile_n=64", {"NX_CUDA_MM_TILE_N": "64"}),
                       ("group=4", {"NX_CUDA_MM_GROUP": "4"}), ("group=16", {"NX_CUDA_MM_GROUP": "16"}),
                       ("group=32", {"NX_CUDA_MM_GROUP": "32"}), ("single-cta", {"NX_CUDA_MM_PAIR": "0"}),
-                      ("wide 256x512", {"NX_CUDA_MM_WIDE": "1"})):
-        for k in ("NX_CUDA_MM_TILE_N", "NX_CUDA_MM_GROUP", "NX_CUDA_MM_PAIR", "NX_CUDA_MM_WIDE"):
+                      ("wide 256x512", {"NX_CUDA_MM_WIDE": "1"}),
+                      ("prefetch=7", {"NX_CUDA_MM_PREFETCH": "7"}), ("prefetch=10", {"NX_CUDA_MM_PREFETCH": "10"}),
+                      ("prefetch=16", {"NX_CUDA_MM_PREFETCH": "16"}), ("prefetch=32", {"NX_CUDA_MM_PREFETCH": "32"})):
+        for k in ("NX_CUDA_MM_TILE_N", "NX_CUDA_MM_GROUP", "NX_CUDA_MM_PAIR", "NX_CUDA_MM_WIDE", "NX_CUDA_MM_PREFETCH"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3):
