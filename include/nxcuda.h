@@ -136,7 +136,9 @@ NXC_API nxc_status nxc_d2h_async(nxc_ctx *ctx, void *dst_host_pinned, const void
    launch, any number of times, on the context's stream.
      - memory: while capturing, nxc_alloc / nxc_free are served by an arena the graph owns, so
        the handles created during the capture keep their addresses and are the replay's outputs;
-       they stay valid until nxc_graph_destroy, and nxc_free of them afterwards is a no-op.
+       nxc_free of one outside the capture only drops the handle. The arena is released when the
+       graph has been destroyed AND the last handle into it has been dropped, in either order (a
+       garbage collector finalises in no particular order).
        Buffers that existed before the capture (inputs, parameters) are read in place by every
        replay: keep them alive and update them in place (nxc_copy into them) between replays.
      - calls that block or read back (nxc_sync, nxc_d2h, the checked gather / scatter range test,

@@ -180,9 +180,9 @@ class _Buffer:
 
     def __del__(self):
         try:
-            # arena memory is recycled only while its capture is still recording; afterwards the
-            # graph owns it (the engine would ignore the call) or has already released it
-            if self.owned and self.ptr and self.ctx._p and (self._graph is None or self.ctx._capturing is self._graph):
+            # (a handle into a captured step's arena is only counted by the engine: the arena lives
+            # until the graph is destroyed AND its last handle is gone, whichever comes last)
+            if self.owned and self.ptr and self.ctx._p:
                 self.ctx._lib.nxc_free(self.ctx.ptr, self.ptr)
         except Exception:
             pass

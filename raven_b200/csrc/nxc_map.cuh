@@ -617,6 +617,129 @@ nxc_map_tiledv_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__
   }
 }
 
+
+// Narrow variant of the vector tiled kernel, for 1- and 2-byte elements: with those the kernel above
+// moves only 4 elements = 4-8 bytes per lane and access (measured 0.44-0.66 of the HBM rate: the LSU
+// is the limit, not memory). Here a tile is 128 x 128 elements, EVERY global access is a 16-byte
+// vector (8 or 16 elements) and every shared-memory access moves at least 4 bytes:
+//   * a transposed operand is stored with 16-byte vector stores, rows unpadded, the 16-byte chunks of
+//     a row XOR-swizzled by (row / V), so that the gather in the other direction -- lane vx reads rows
+//     vx*V + q, V rows apart -- finds its 16 (8) lanes in 16 (8) different chunks;
+//   * the gather reads 32-bit WORDS: a word holds the same source row's elements for W = 2 (4)
+//     adjacent output rows, so a thread produces W output vectors at once and issues V word loads
+//     for them instead of W*V sub-word ones.
+template <class K> struct NxcTiledN {
+  static constexpr int ESZ = (int)sizeof(typename K::S0);
+  static constexpr int T = 128;
+  static constexpr int V = 16 / ESZ;      // elements per 16-byte vector
+  static constexpr int W = 4 / ESZ;       // elements per 32-bit word = output rows a thread produces per pass
+  static constexpr int CPR = T / V;       // 16-byte chunks (= vector lanes) per tile row
+  static constexpr int RP = 256 / CPR;    // thread rows
+  static constexpr int NPL = T / RP;      // load passes (one tile row per thread row and pass)
+  static constexpr int NPO = T / (RP * W);  // output passes (W tile rows per thread row and pass)
+  static constexpr int TILE_BYTES = T * T * ESZ;
+};
+
+template <class K>
+__global__ void __launch_bounds__(256)
+nxc_map_tiledn_kernel(typename K::S0 *__restrict__ out, const typename K::S1 *__restrict__ a,
+                      const typename K::S2 *__restrict__ b, const typename K::S3 *__restrict__ c,
+                      const __grid_constant__ NxcTiledArgs<K::NIN + 1> g, typename K::P prm) {
+  typedef typename K::S0 S0; typedef typename K::S1 S1; typedef typename K::S2 S2; typedef typename K::S3 S3;
+  typedef NxcTiledN<K> C;
+  constexpr int NOP = K::NIN + 1;
+  constexpr int T = C::T, V = C::V, W = C::W, CPR = C::CPR, RP = C::RP, NPL = C::NPL, NPO = C::NPO, ESZ = C::ESZ;
+  static_assert(K::NIN >= 1 && K::NIN <= 2, "tiled ops have one or two inputs");
+  extern __shared__ __align__(16) unsigned char nxc_tiledn_smem[];
+  const int vx = threadIdx.x % CPR, ry = threadIdx.x / CPR;
+  uint32_t t = blockIdx.x;
+  const uint32_t rest = nxc_fastdiv(t, g.tiles_ij_div);
+  t -= rest * g.tiles_ij_div.d;
+  const uint32_t tj = nxc_fastdiv(t, g.tiles_i_div);
+  const uint32_t ti = t - tj * g.tiles_i_div.d;
+  int64_t base[NOP];
+#pragma unroll
+  for (int k = 0; k < NOP; k++) base[k] = 0;
+  {
+    uint32_t r = rest;
+    for (int d = g.nrest - 1; d >= 0; d--) {
+      uint32_t q = nxc_fastdiv(r, g.rest_div[d]);
+      uint32_t cd = r - q * g.rest_div[d].d;
+#pragma unroll
+      for (int k = 0; k < NOP; k++) base[k] += (int64_t)cd * g.rest_stride[k][d];
+      r = q;
+    }
+  }
+  const uint32_t j0 = tj * T, i0 = ti * T;
+  constexpr int KA = 1 < NOP ? 1 : 0, KB = 2 < NOP ? 2 : 0;
+  const bool a_t = (g.tmask & 2u) != 0, b_t = K::NIN >= 2 && (g.tmask & 4u) != 0;
+  unsigned char *ta = nxc_tiledn_smem, *tb = nxc_tiledn_smem + (a_t ? C::TILE_BYTES : 0);  // one tile per TRANSPOSED operand
+  // byte offset of the 16-byte chunk `chunk` of tile row `row` in a swizzled tile
+  auto chunk_at = [](int row, int chunk) { return row * (T * ESZ) + ((chunk ^ ((row / V) % CPR)) << 4); };
+  // transposed operands: 16-byte vectors along J at fixed i, straight into shared memory
+#pragma unroll
+  for (int r = 0; r < NPL; r++) {
+    const uint32_t il = ry + RP * r, gi = i0 + il, gj = j0 + vx * V;
+    if (gi < g.SI && gj < g.SJ) {
+      if (a_t) *reinterpret_cast<uint4 *>(ta + chunk_at(il, vx)) =
+          __ldg(reinterpret_cast<const uint4 *>(a + base[KA] + (int64_t)gj + (int64_t)gi * g.si[KA]));
+      if (b_t) *reinterpret_cast<uint4 *>(tb + chunk_at(il, vx)) =
+          __ldg(reinterpret_cast<const uint4 *>(b + base[KB] + (int64_t)gj + (int64_t)gi * g.si[KB]));
+    }
+  }
+  __syncthreads();
+  // output: thread (vx, ry) produces, per pass, the W rows jl0 .. jl0 + W - 1 of output vector vx
+#pragma unroll 1
+  for (int r = 0; r < NPO; r++) {
+    const uint32_t jl0 = (ry + RP * r) * W, gi = i0 + vx * V;
+    if (gi >= g.SI || j0 + jl0 >= g.SJ) continue;   // SJ is a multiple of V >= W: the W rows are all in or all out
+    S1 ea[W][V]; S2 eb[W][V];
+    // straight operands: a 16-byte vector along I per output row (stride 1) or one broadcast element
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+      const int64_t gj = (int64_t)j0 + jl0 + w;
+      if (!a_t) {
+        const S1 *p = a + base[KA] + gj * g.sj[KA];
+        if (g.si[KA] == 0) { S1 sv = p[0]; _Pragma("unroll") for (int q = 0; q < V; q++) ea[w][q] = sv; }
+        else nxc_load_vec<S1, V>(p + gi, ea[w]);
+      }
+      if (K::NIN >= 2 && !b_t) {
+        const S2 *p = b + base[KB] + gj * g.sj[KB];
+        if (g.si[KB] == 0) { S2 sv = p[0]; _Pragma("unroll") for (int q = 0; q < V; q++) eb[w][q] = sv; }
+        else nxc_load_vec<S2, V>(p + gi, eb[w]);
+      }
+    }
+    // transposed operands: V word gathers, each word = W adjacent output rows of source row vx*V + q
+    if (a_t || b_t) {
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        const int off = chunk_at(vx * V + q, (int)jl0 / V) + ((int)jl0 % V) * ESZ;
+        if (a_t) {
+          union { uint32_t u; S1 e[W]; } wa;
+          wa.u = *reinterpret_cast<const uint32_t *>(ta + off);
+#pragma unroll
+          for (int w = 0; w < W; w++) ea[w][q] = wa.e[w];
+        }
+        if (b_t) {
+          union { uint32_t u; S2 e[W]; } wb;
+          wb.u = *reinterpret_cast<const uint32_t *>(tb + off);
+#pragma unroll
+          for (int w = 0; w < W; w++) eb[w][q] = wb.e[w];
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+      S0 vo[V];
+      S3 ec[V];
+#pragma unroll
+      for (int q = 0; q < V; q++) { ec[q] = S3(); if (K::NIN < 2) eb[w][q] = S2(); }
+      nxc_run_vec<K, V>(ea[w], eb[w], ec, vo, prm);
+      nxc_store_vec<S0, V>(out + base[0] + ((int64_t)j0 + jl0 + w) * g.sj[0] + gi, vo);
+    }
+  }
+}
+
 // Host side: does this plan want the tiled kernel? Picks J = the dim on which some input has
 // unit stride while the output's unit stride is on the last dim.
 template <class K, bool ENABLED> struct NxcTiledLaunch {
@@ -626,9 +749,8 @@ template <class K> struct NxcTiledLaunch<K, true> {
   // every access of the vector kernel is a V-element vector: extents, the strides that move
   // between vectors, and the bases must all be V-aligned, and straight operands must run
   // along I with stride 1 (or broadcast along it)
-  static bool nxc_tiledv_ok(const NxcMapPlan &p, int J, uint32_t tmask) {
+  template <int V> static bool nxc_tiled_vec_ok(const NxcMapPlan &p, int J, uint32_t tmask) {
     constexpr int NOP = K::NIN + 1;
-    constexpr int V = NxcTiledV<K>::V;
     const int I = p.ndim - 1;
     if (K::NIN > 2 || p.shape[I] % V || p.shape[J] % V) return false;
     const size_t esz[4] = {sizeof(typename K::S0), sizeof(typename K::S1), sizeof(typename K::S2), sizeof(typename K::S3)};
@@ -677,7 +799,33 @@ template <class K> struct NxcTiledLaunch<K, true> {
     if (blocks >= 0x7FFFFFFFLL) return false;
     g.tiles_i_div = nxc_fastdiv_make(g.tiles_i);
     g.tiles_ij_div = nxc_fastdiv_make(g.tiles_i * g.tiles_j);
-    if (nxc_tiledv_ok(p, J, tmask)) {
+    if constexpr (sizeof(S0) <= 2 && K::NIN >= 1) {
+      if (nxc_tiled_vec_ok<NxcTiledN<K>::V>(p, J, tmask)) {
+        typedef NxcTiledN<K> CN;
+        constexpr int T = CN::T;
+        g.tiles_j = (g.SJ + T - 1) / T;
+        g.tiles_i = (g.SI + T - 1) / T;
+        g.tiles_i_div = nxc_fastdiv_make(g.tiles_i);
+        g.tiles_ij_div = nxc_fastdiv_make(g.tiles_i * g.tiles_j);
+        const int64_t nblocks = nrest_total * g.tiles_j * g.tiles_i;
+        constexpr int smem_max = K::NIN * CN::TILE_BYTES;
+        const int smem = (((tmask >> 1) & 1) + ((tmask >> 2) & 1)) * CN::TILE_BYTES;
+        static bool attr_done = false;   // per instantiation; one device per process
+        if (!attr_done && smem_max > 48 * 1024) {
+          cudaError_t ae = cudaFuncSetAttribute(nxc_map_tiledn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+          if (ae != cudaSuccess) { *st = nxc_cuda_fail(ctx, ae, "cudaFuncSetAttribute"); return true; }
+          attr_done = true;
+        }
+        nxc_map_tiledn_kernel<K><<<(unsigned)nblocks, 256, smem, ctx->stream>>>(
+            (S0 *)p.base[0], (const S1 *)(NOP > 1 ? p.base[1] : p.base[0]), (const S2 *)(NOP > 2 ? p.base[2] : p.base[0]),
+            (const S3 *)(NOP > 3 ? p.base[3] : p.base[0]), g, prm);
+        ctx->launches++;
+        cudaError_t e = cudaPeekAtLastError();
+        *st = (e == cudaSuccess) ? NXC_OK : nxc_cuda_fail(ctx, e, "kernel launch");
+        return true;
+      }
+    }
+    if (nxc_tiled_vec_ok<NxcTiledV<K>::V>(p, J, tmask)) {
       constexpr int T = NxcTiledV<K>::T;
       g.tiles_j = (g.SJ + T - 1) / T;
       g.tiles_i = (g.SI + T - 1) / T;

@@ -38,6 +38,8 @@ struct nxc_graph {
   std::map<char *, std::pair<size_t, int>> live;    // ptr -> (size, chunk)
   uint64_t kernels = 0;                             // kernel nodes = launches per replay
   size_t arena_bytes = 0, peak_live = 0, now_live = 0;
+  size_t internal = 0;                              // live blocks the engine itself holds (scratch): not handles
+  bool destroyed = false;                           // nxc_graph_destroy was called; the arena waits for its handles
   bool owns(const void *p) const {
     for (const Chunk &c : chunks)
       if ((const char *)p >= c.base && (const char *)p < c.base + c.size) return true;
@@ -97,6 +99,7 @@ static void arena_free(nxc_graph *g, void *ptr) {
   }
   g->free_[p] = {size, chunk};
 }
+static void graph_forget(nxc_ctx *ctx, nxc_graph *g);
 static nxc_graph *graph_owning(nxc_ctx *ctx, const void *p) {
   for (int i = 0; i < ctx->n_graphs; i++)
     if (ctx->graphs[i]->owns(p)) return ctx->graphs[i];
@@ -234,7 +237,7 @@ extern "C" void nxc_ctx_destroy(nxc_ctx *ctx) {
     cudaEventDestroy(ctx->ev_comm);
   }
   free(ctx->pending);
-  while (ctx->n_graphs > 0) nxc_graph_destroy(ctx, ctx->graphs[ctx->n_graphs - 1]);
+  while (ctx->n_graphs > 0) graph_forget(ctx, ctx->graphs[ctx->n_graphs - 1]);
   free(ctx->graphs);
   if (ctx->hstatus) cudaFreeHost((void *)ctx->hstatus);
   if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
@@ -327,7 +330,17 @@ extern "C" nxc_status nxc_free(nxc_ctx *ctx, void *dptr) {
     arena_free(ctx->capturing, dptr);
     return NXC_OK;
   }
-  if (ctx->n_graphs && graph_owning(ctx, dptr)) return NXC_OK;  // a replay output: the graph owns it
+  if (ctx->n_graphs) {
+    // A handle created during a capture (a replay's output). The graph owns the memory; the handle's
+    // release is only COUNTED, so that a graph destroyed before its handles (finalisers run in no
+    // particular order under a GC) keeps its arena until the last of them is gone -- a stale arena
+    // address must never reach cudaFreeAsync, it may by then belong to somebody else.
+    if (nxc_graph *g = graph_owning(ctx, dptr)) {
+      g->live.erase((char *)dptr);
+      if (g->destroyed && g->live.size() <= g->internal) graph_forget(ctx, g);
+      return NXC_OK;
+    }
+  }
   if (ctx->n_pending) {
     nxc_reap_pending(ctx, false);
     bool owned = false;
@@ -441,6 +454,7 @@ nxc_status nxc_scratch(nxc_ctx *ctx, size_t bytes, void **out) {
     size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
     nxc_status s = arena_alloc(ctx, ctx->capturing, want, &p);
     if (s) return s;
+    ctx->capturing->internal++;
     ctx->scratch = p;
     ctx->scratch_bytes = want;
   }
@@ -474,11 +488,21 @@ extern "C" nxc_status nxc_capture_begin(nxc_ctx *ctx) {
 }
 
 static void graph_release(nxc_ctx *ctx, nxc_graph *g) {
+  (void)ctx;
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   for (const nxc_graph::Chunk &c : g->chunks) cudaFree(c.base);
   cudaGetLastError();
   delete g;
+}
+// drop a graph from the context's list and free its arena
+static void graph_forget(nxc_ctx *ctx, nxc_graph *g) {
+  for (int i = 0; i < ctx->n_graphs; i++)
+    if (ctx->graphs[i] == g) {
+      ctx->graphs[i] = ctx->graphs[--ctx->n_graphs];
+      break;
+    }
+  graph_release(ctx, g);
 }
 
 extern "C" nxc_status nxc_capture_end(nxc_ctx *ctx, nxc_graph **out) {
@@ -534,6 +558,10 @@ extern "C" nxc_status nxc_capture_end(nxc_ctx *ctx, nxc_graph **out) {
 
 extern "C" nxc_status nxc_graph_launch(nxc_ctx *ctx, nxc_graph *g) {
   if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_graph_launch");
+  if (!g || g->destroyed || !g->exec) {
+    snprintf(ctx->err, sizeof ctx->err, "%s: nxc_graph_launch of a destroyed graph", NXC_ERR_CUDA);
+    return NXC_ERR_CUDA;
+  }
   NXC_CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
   ctx->launches += g->kernels;
   return NXC_OK;
@@ -542,14 +570,13 @@ extern "C" uint64_t nxc_graph_kernels(nxc_graph *g) { return g->kernels; }
 extern "C" size_t nxc_graph_arena_bytes(nxc_graph *g) { return g->arena_bytes; }
 
 extern "C" void nxc_graph_destroy(nxc_ctx *ctx, nxc_graph *g) {
-  if (!g) return;
+  if (!g || g->destroyed) return;
   cudaStreamSynchronize(ctx->stream);  // no replay may still be running on the arena
-  for (int i = 0; i < ctx->n_graphs; i++)
-    if (ctx->graphs[i] == g) {
-      ctx->graphs[i] = ctx->graphs[--ctx->n_graphs];
-      break;
-    }
-  graph_release(ctx, g);
+  g->destroyed = true;
+  if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = NULL; }
+  if (g->graph) { cudaGraphDestroy(g->graph); g->graph = NULL; }
+  // the arena goes when the last handle into it has been released (see nxc_free); at once if none is left
+  if (g->live.size() <= g->internal) graph_forget(ctx, g);
 }
 
 // ---- the map plan ---------------------------------------------------------------

@@ -45,3 +45,30 @@ def test_reference_arm_line():
     assert b["impl"] == "reference" and b["gpu_launches"] == 0
     assert b["e2e"] == {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert b["cpu_baseline"]["kind"] == "reference" and b["cpu_baseline"]["value"] == b["value"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 8])
+def test_round2_cuda_arm_line(n):
+    """Round 2's lines: the same contract plus what round 1's verdict asked for -- asserts made in the
+    run, measured traffic, the reference arm's configuration, configs[3] / configs[4] keys."""
+    b = _line(f"bench_r02_n{n}.json")
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert b["metric"] == base["metric"] and b["unit"] == "GB/s" and b["n_gpus"] == n and b["impl"] == "cuda"
+    per_gpu = b["config"]["algorithmic_bytes_per_step_per_gpu"]
+    assert abs(b["value"] - n * per_gpu / (b["ms_per_step"] * 1e-3) / 1e9) <= 0.01 * b["value"]
+    assert b["gpu_launches"] > 0 and "captured" in b["config"]["issue"]
+    c = b["checks"]
+    assert c["replay_equals_eager"] and c["argmax_vs_closed_form"] and c["e2e_readbacks_match_host"]
+    if n > 1:
+        assert c["planted_max_on_last_rank"] and c["nan_on_rank1_wins_and_sticks"] and c["bit_identical_across_ranks"]
+    e = b["e2e"]
+    assert e["d2h_bytes_per_step"] >= 3 * (per_gpu // 48) * 4        # all three elementwise results come back
+    assert b["cpu_baseline"]["kind"] == "reference" and "2^28" in b["cpu_baseline"]["sample"]
+    if n == 1:
+        r = b["roofline"]
+        assert r["traffic"] and "this run" in r["traffic_source"]
+        assert 0.9 * r["algorithmic_bytes_per_launch"] < r["traffic"] < 1.1 * r["algorithmic_bytes_per_launch"]
+        assert b["matmul"]["check"]["worst_error_over_bound"] <= 1.0
+        assert b["mlp_grad"]["bf16"]["captured_loss_equals_eager"]
+    g = b["gpt2_step"]
+    assert g["reference_protocol_4x64"]["launches_per_step"] > 1000 and g["bf16_8x1024"]["ms_per_step"] > 0

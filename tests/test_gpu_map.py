@@ -276,3 +276,34 @@ def test_rank32(ctx, oracle):
     perm[0], perm[1] = 1, 0
     got = H.download(B.add(B.permute(H.upload(ctx, a), perm), H.upload(ctx, b)))
     assert got.reshape(-1).tolist() == [11, 23, 32, 44]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "i8", "u8", "i16", "u16", "bool"])
+def test_transposed_views_of_narrow_dtypes(ctx, oracle, dtype):
+    """The 128 x 128 swizzled-tile kernel for 1- and 2-byte elements (nxc_map_tiledn_kernel): one or
+    both operands transposed, extents that are and are not multiples of the tile (but of the 16-byte
+    vector), a batch dim, a row-broadcast straight operand, contiguous(transpose); and extents that
+    do not divide the vector, which must fall back to the other tiled kernels. Bit-exact."""
+    rng = np.random.default_rng(31)
+    ops = ("max",) if dtype == "bool" else ("add", "mul")
+    for (R, Cc) in [(256, 384), (144, 208), (130, 100), (48, 1040)]:
+        a = H.HostView(_rand(dtype, R * Cc, rng), dtype, [R, Cc])
+        at = H.HostView(_rand(dtype, R * Cc, rng), dtype, [Cc, R]).permute([1, 0])
+        bt = H.HostView(_rand(dtype, R * Cc, rng), dtype, [Cc, R]).permute([1, 0])
+        row = H.HostView(_rand(dtype, Cc, rng), dtype, [1, Cc]).expand([R, Cc])
+        for op in ops:
+            for name, (x, y) in {"a + bT": (a, at), "aT + bT": (at, bt), "aT + row": (at, row)}.items():
+                want = oracle.binary(op, x, y).numpy()
+                got = H.download(getattr(B, op)(H.upload(ctx, x), H.upload(ctx, y)))
+                H.assert_same(dtype, got, want, ulp=0, what=f"{op}/{dtype}/{R}x{Cc}/{name}")
+        want = oracle.copy(at).numpy()
+        got = H.download(B.contiguous(H.upload(ctx, at)))
+        assert np.array_equal(H.raw(got), H.raw(want)), f"contiguous(transpose)/{dtype}/{R}x{Cc}"
+    # batched: [3, R, C] + transposed-in-the-last-two-dims view of [3, C, R]
+    R, Cc = 160, 272
+    a3 = H.HostView(_rand(dtype, 3 * R * Cc, rng), dtype, [3, R, Cc])
+    b3 = H.HostView(_rand(dtype, 3 * R * Cc, rng), dtype, [3, Cc, R]).permute([0, 2, 1])
+    op = ops[0]
+    want = oracle.binary(op, a3, b3).numpy()
+    got = H.download(getattr(B, op)(H.upload(ctx, a3), H.upload(ctx, b3)))
+    H.assert_same(dtype, got, want, ulp=0, what=f"{op}/{dtype}/batched transposed")

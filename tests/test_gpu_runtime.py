@@ -51,3 +51,31 @@ def test_async_readback_needs_pinned(ctx):
     t = B.full(ctx, DT.float32, [1 << 10], 1.0)
     with pytest.raises(Failure, match="pinned"):
         B.to_host_async(t, np.empty(1 << 10, np.float32))
+
+
+def test_two_readbacks_of_one_buffer_then_drop(ctx):
+    """Two asynchronous read-backs of the SAME tensor, then the tensor is dropped: the buffer must
+    outlive the LAST copy, not the first (the engine releases it with the last pending entry)."""
+    n = 1 << 23   # 32 MiB: the second copy is still queued when the first finishes
+    a = B.contiguous(B.expand(B.full(ctx, DT.float32, [], 3.5), [n]))
+    o1, o2 = ctx.pinned_empty(n, np.float32), ctx.pinned_empty(n, np.float32)
+    B.to_host_async(a, o1)
+    B.to_host_async(a, o2)
+    del a
+    for _ in range(6):   # churn: same-sized buffers of another value, allocated while the copies run
+        junk = B.contiguous(B.expand(B.full(ctx, DT.float32, [], -1.0), [n]))
+        del junk
+    ctx.sync()
+    assert (o1 == 3.5).all() and (o2 == 3.5).all()
+
+
+def test_unchecked_gather_reports_at_the_next_sync(ctx):
+    """nxc_gather_trusted does not drain the stream; an out-of-range index is never dereferenced and
+    its flag is sticky in the status page until nxc_sync / nxc_d2h reports it -- once."""
+    data = B.full(ctx, DT.float32, [8, 4], 2.0)
+    idx = B.reshape(B.from_host(ctx, np.array([0, 1, 99, 3, 4, 5, 6, 7], dtype=np.int32)), [2, 4])
+    out = B.gather(data, idx, 0, trusted=True)
+    with pytest.raises(Failure, match="index out of bounds"):
+        ctx.sync()
+    ctx.sync()
+    assert B.to_numpy(out).shape == (2, 4)
