@@ -632,6 +632,8 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
   // 1- and 2-byte elements: a 16 K-element row is only 16-32 KB, so a block per row spends as long in
   // its barrier-and-shuffle epilogue as in its loads (bf16 / i8 inner-axis sums of [16384, 16384]:
   // 0.75 / 0.49 of the HBM rate). With rows to spare a warp walks the whole row instead.
+  // (spreading a row over 2-4 warps to get more blocks for the SMs to balance was tried: 0.72 against
+  // 0.77 for bf16 rows of 16384 -- the block barrier in the row epilogue costs more than the tail)
   if (tl > 5 && sizeof(S) <= 2 && items <= 2048 && p.nr <= 1 && p.nk <= 1 && p.O >= (int64_t)ctx->sm_count * 64) tl = 5;
   // ... and with rows to spare, fewer lanes per row, 8 work items each: the per-row epilogue (a
   // shuffle butterfly, for argreduce also the index vote) is paid per thread GROUP, and at 32 lanes
