@@ -89,9 +89,14 @@ def check_reduce():
                 continue
             if dtype in H.COMPLEX and op in ("max", "min"):
                 continue
-            for axes, rows, cols in (([0], 6, 40), ([0, 1], 6, 40), ([1], 6, 40), ([0], 3, 70000)):
-                if cols == 70000 and (dtype not in ("f32", "i32", "i16") or op not in ("sum", "max")):
-                    continue   # > 256 KiB of partials: the NCCL / gather path behind the mailbox limit
+            for axes, rows, cols in (([0], 6, 40), ([0, 1], 6, 40), ([1], 6, 40), ([0], 3, 70000), ([0], 2, 200000)):
+                # 70000 / 200000 columns: partials above the 256 KiB mailbox slot -> NCCL where it has the
+                # reduction (f32 / i32 sum), all-gather + the backend's own fold where it has not (int16,
+                # NaN-sticky float max)
+                if cols == 70000 and (dtype not in ("f32", "i32") or op not in ("sum", "max")):
+                    continue
+                if cols == 200000 and (dtype, op) not in (("i16", "sum"), ("i16", "max"), ("bf16", "max"), ("f32", "min")):
+                    continue
                 span = (0.6, 1.4) if op == "prod" else (-4.0, 4.0)
                 full, slab = full_and_slab(dtype, rows, cols, rng, *span)
                 got = H.download(sharded.sharded_reduce(H.upload(ctx, slab), op, axes, comm))
@@ -234,8 +239,39 @@ def check_capture():
     checks += 1
 
 
+def check_dp_training():
+    """Kaun-style data parallelism end to end (reference: packages/kaun/test/test_pmap_dp.ml:18 compares
+    the multi-device trajectory with the single-device one): a tiny GPT-2 trained for a few SGD steps
+    with the batch sharded over the ranks and gradients averaged through FlatBucketReducer must follow
+    the single-GPU run on the whole batch -- losses and final parameters, to f32 reduction order."""
+    global checks
+    from tools import gpt2_step as G
+    cfg, per_rank, seq = G.GPT2_TINY, 2, 12
+    grid = np.random.default_rng(321).integers(0, cfg["vocab"], (per_rank * world, seq + 1))
+    host = G.init_params_host(cfg, seed=11)
+    dp = G.Trainer(B, ctx, cfg, per_rank, seq, opt="sgd", lr=5e-2, comm=comm, bucket_mb=0, host_params={k: v.copy() for k, v in host.items()})
+    dp.bucket_bytes = 16 << 10   # several buckets even at this size
+    mine = grid[rank * per_rank:(rank + 1) * per_rank]
+    dp.set_batch(mine[:, :-1], mine[:, 1:])
+    one = G.Trainer(B, ctx, cfg, per_rank * world, seq, opt="sgd", lr=5e-2, comm=None, host_params={k: v.copy() for k, v in host.items()})
+    one.set_batch(grid[:, :-1], grid[:, 1:])
+    for step in range(4):
+        dp.pre_step()
+        one.pre_step()
+        l_dp = sharded.allreduce_mean_([dp.step_body()], comm)[0]
+        l_one = one.step_body()
+        a, b = float(H.download(l_dp)), float(H.download(l_one))
+        assert abs(a - b) <= 1e-5 * abs(b), f"step {step}: data-parallel loss {a} vs single-GPU {b}"
+    for k in one.params:
+        w, g = H.download(one.params[k]).astype(np.float64), H.download(dp.params[k]).astype(np.float64)
+        assert np.abs(w - g).max() <= 1e-5 * (np.abs(w).max() + 1e-3), f"parameter {k} diverged"
+        same_on_all_ranks(H.download(dp.params[k]), k)
+    checks += 1
+
+
 try:
     check_reduce()
+    check_dp_training()
     check_argreduce()
     check_batch_matmul_and_dp()
     check_capture()
