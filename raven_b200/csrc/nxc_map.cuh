@@ -131,7 +131,12 @@ template <class K> struct NxcKInfo {
   // 64 (a thread's 16-byte loads of one operand then stay within two 32-byte sectors' reach of
   // its neighbours'; 8-byte -> bool at 16 items per thread measured 0.71 of the f32 rate)
   static constexpr int IPT_RAW = 16 / min_size;
-  static constexpr int IPT = IPT_RAW * max_size > 64 ? 64 / max_size : IPT_RAW;
+  // A cast whose sides differ 4x or more in width (i8 <-> f32, i16 <-> f64 ...): let the WIDE side move
+  // 16 bytes per lane -- the warp's wide accesses are then one contiguous 512 bytes and the narrow ones
+  // one contiguous 128 -- instead of the narrow side (one 16-byte load feeding four 16-byte stores 64
+  // bytes apart from lane to lane: every store instruction touched 32 quarter-filled segments, 0.70).
+  static constexpr bool WIDE_SIDE = K::NIN == 1 && max_size >= 4 * min_size;
+  static constexpr int IPT = WIDE_SIDE ? 16 / max_size : (IPT_RAW * max_size > 64 ? 64 / max_size : IPT_RAW);
   // independent steps in flight: aim at 64 bytes of the largest type per thread
   // ... and at least 32 bytes of the SMALLEST: a widening cast (i8 -> f32: one 16-byte load feeding
   // four 16-byte stores) otherwise keeps a single load in flight per thread (measured 0.70)
