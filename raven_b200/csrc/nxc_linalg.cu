@@ -136,6 +136,81 @@ __global__ void __launch_bounds__(NXC_LA_THREADS) nxc_cholesky_kernel(T *work, i
   }
 }
 
+// ---- blocked cholesky for large real matrices ----------------------------------------------------
+// One CTA per matrix is the right shape for the batched small systems the reference's callers
+// issue; a single 512 x 512 matrix took 25 ms that way.  Large real matrices go right-looking in
+// panels of NXC_CH_NB columns: (1) the diagonal block is factored in shared memory by one CTA per
+// matrix, (2) the panel below it is solved row by row against that block, one thread per row,
+// (3) the trailing update A22 -= L21 L21^T is a product through nxc_matmul plus one strided
+// subtract -- all on views of the same work matrix, no block is copied out.  Same contract as the
+// kernel above: lower triangle read, status 1 when a pivot is not > 0.
+#define NXC_CH_NB 64
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_chol_diag_kernel(T *work, int64_t n, int64_t j0, int nb, int *status) {
+  __shared__ T S[NXC_CH_NB][NXC_CH_NB + 1];
+  __shared__ int bad;
+  T *A = work + (int64_t)blockIdx.x * n * n + j0 * n + j0;
+  if (threadIdx.x == 0) bad = 0;
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) S[e / nb][e % nb] = A[(int64_t)(e / nb) * n + e % nb];
+  __syncthreads();
+  for (int j = 0; j < nb; j++) {
+    if (threadIdx.x == 0) {
+      const T d = S[j][j];
+      if (!(d > (T)0)) { bad = 1; atomicExch(status, 1); }
+      else S[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    if (bad) return;
+    const T ljj = S[j][j];
+    for (int i = j + 1 + threadIdx.x; i < nb; i += blockDim.x) S[i][j] = S[i][j] / ljj;
+    __syncthreads();
+    const int t = nb - 1 - j;
+    for (int e = threadIdx.x; e < t * t; e += blockDim.x) {
+      const int i = j + 1 + e / t, c = j + 1 + e % t;
+      if (c <= i) S[i][c] -= S[i][j] * S[c][j];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x)
+    if (e % nb <= e / nb) A[(int64_t)(e / nb) * n + e % nb] = S[e / nb][e % nb];
+}
+
+// rows below a full diagonal block: x L11^T = a, forward over the block's columns
+template <class T>
+__global__ void __launch_bounds__(128) nxc_chol_panel_kernel(T *work, int64_t n, int64_t j0) {
+  __shared__ T S[NXC_CH_NB][NXC_CH_NB + 1];
+  T *M = work + (int64_t)blockIdx.y * n * n;
+  for (int e = threadIdx.x; e < NXC_CH_NB * NXC_CH_NB; e += blockDim.x)
+    S[e / NXC_CH_NB][e % NXC_CH_NB] = M[(j0 + e / NXC_CH_NB) * n + j0 + e % NXC_CH_NB];
+  __syncthreads();
+  const int64_t row = j0 + NXC_CH_NB + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  T *a = M + row * n + j0;
+  T x[NXC_CH_NB];
+#pragma unroll
+  for (int c = 0; c < NXC_CH_NB; c++) {
+    T v = a[c];
+#pragma unroll
+    for (int k = 0; k < c; k++) v -= x[k] * S[c][k];
+    x[c] = v / S[c][c];
+  }
+#pragma unroll
+  for (int c = 0; c < NXC_CH_NB; c++) a[c] = x[c];
+}
+
+// the other triangle: zeros for ~lower; ~upper moves L to L^T and zeroes below
+template <class T>
+__global__ void __launch_bounds__(256) nxc_chol_finish_kernel(T *work, int64_t n, int upper) {
+  T *M = work + (int64_t)blockIdx.y * n * n;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int64_t i = e / n, c = e % n;
+  if (c >= i) return;
+  if (upper) { M[c * n + i] = M[i * n + c]; M[i * n + c] = (T)0; }
+  else M[c * n + i] = (T)0;
+}
+
 // ---- triangular solve: op(A) X = B in place on X (n x nrhs), A n x n ----------------------------
 template <class T>
 __global__ void __launch_bounds__(NXC_LA_THREADS)
@@ -321,6 +396,46 @@ static nxc_status nxc_la_fail(nxc_ctx *ctx, nxc_status s) {
     default: { typedef cf64 T; __VA_ARGS__ } break;                       \
   }
 
+// blocked factorisation of the contiguous work matrices w [batch..., n, n] (real dtypes)
+template <class T>
+static nxc_status nxc_cholesky_blocked(nxc_ctx *ctx, const nxc_tensor *w, int64_t n, int64_t nbatch, int upper, int *st) {
+  nxc_status s = NXC_OK;
+  const int nd = w->ndim;
+  for (int64_t j0 = 0; j0 < n && !s; j0 += NXC_CH_NB) {
+    const int nb = (int)(n - j0 < NXC_CH_NB ? n - j0 : NXC_CH_NB);
+    nxc_chol_diag_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)w->data, n, j0, nb, st);
+    ctx->launches++;
+    const int64_t m = n - j0 - nb;
+    if (m <= 0) break;
+    nxc_chol_panel_kernel<T><<<dim3((unsigned)((m + 127) / 128), (unsigned)nbatch), 128, 0, ctx->stream>>>((T *)w->data, n, j0);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) return nxc_cuda_fail(ctx, cudaGetLastError(), "cholesky panel");
+    // A22 -= L21 L21^T on views of the work matrix
+    nxc_tensor l21 = *w, l21t = *w, a22 = *w, prod;
+    void *pbuf = NULL;
+    l21.offset = (j0 + nb) * n + j0;  l21.shape[nd - 2] = m;  l21.shape[nd - 1] = nb;
+    l21t = l21;  l21t.shape[nd - 2] = nb;  l21t.shape[nd - 1] = m;  l21t.strides[nd - 2] = 1;  l21t.strides[nd - 1] = n;
+    a22.offset = (j0 + nb) * n + (j0 + nb);  a22.shape[nd - 2] = m;  a22.shape[nd - 1] = m;
+    if ((s = nxc_la_work(ctx, w, w->dtype, m, m, &prod, &pbuf))) return s;
+    s = nxc_matmul(ctx, &prod, &l21, &l21t);
+    if (!s) s = nxc_map2(ctx, NXC_SUB, &a22, &a22, &prod);
+    nxc_free(ctx, pbuf);
+  }
+  if (s) return s;
+  nxc_chol_finish_kernel<T><<<dim3((unsigned)((n * n + 255) / 256), (unsigned)nbatch), 256, 0, ctx->stream>>>((T *)w->data, n, upper);
+  ctx->launches++;
+  if (cudaPeekAtLastError() != cudaSuccess) return nxc_cuda_fail(ctx, cudaGetLastError(), "cholesky");
+  return NXC_OK;
+}
+
+// where the panel form wins: measured on B200 (profiles/linalg_blocked_r02.json)
+static bool nxc_cholesky_use_blocked(int cdt, int64_t n, int64_t nbatch) {
+  if (cdt != NXC_F32 && cdt != NXC_F64) return false;  // complex keeps the one-CTA kernel (no conj-transposed product)
+  if (getenv("NX_CUDA_CHOLESKY_BLOCKED")) return atoi(getenv("NX_CUDA_CHOLESKY_BLOCKED")) != 0 && n > NXC_CH_NB;
+  (void)nbatch;  // the panel form also wins batched: 16 x 256^2 0.40 ms against 2.8 ms
+  return n >= 128;
+}
+
 extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *in, int upper) {
   NXC_TRACE(ctx, "nxc_cholesky");
   if (nxc_is_capturing(ctx)) return nxc_capture_refuse(ctx, "nxc_cholesky (reads a status word back)");
@@ -345,7 +460,10 @@ extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nx
   s = nxc_alloc(ctx, sizeof(int), (void **)&st);
   if (!s) s = nxc_memset(ctx, st, 0, sizeof(int));
   if (!s) s = nxc_la_move(ctx, &w, in);
-  if (!s) {
+  if (!s && nxc_cholesky_use_blocked(cdt, n, nbatch)) {
+    s = cdt == NXC_F32 ? nxc_cholesky_blocked<float>(ctx, &w, n, nbatch, upper, st)
+                       : nxc_cholesky_blocked<double>(ctx, &w, n, nbatch, upper, st);
+  } else if (!s) {
     NXC_LA_DISPATCH(cdt, { nxc_cholesky_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)buf, n, upper, st); })
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "cholesky");

@@ -127,3 +127,35 @@ def test_linalg_errors(ctx):
     # a unit-diagonal solve never looks at the (zero) diagonal
     x = H.download(B.triangular_solve(up(np.zeros((3, 3)), "f64"), up(np.ones((3, 2)), "f64"), unit_diag=True))
     assert np.array_equal(x, np.ones((3, 2)))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_cholesky_blocked_large(ctx, oracle, dt, monkeypatch):
+    """Large real matrices take the panel-blocked path (nxc_linalg.cu, nxc_cholesky_blocked): checked
+    against the oracle at 320 (ragged last panel) and 512, lower and upper, a small batch, against
+    the one-CTA kernel on the same input, and through the residual at 2048."""
+    rng = np.random.default_rng(45)
+    npdt = np.float32 if dt == "f32" else np.float64
+    for bshape, n in (((), 320), ((2,), 512)):
+        a = rng.standard_normal(bshape + (n, n))
+        spd = hv_of((a @ np.swapaxes(a, -1, -2) / n + np.eye(n)).astype(npdt), dt)
+        for upper in (False, True):
+            want = _wide(oracle, oracle.cholesky(spd, upper))
+            got = _dev_wide(oracle, B.cholesky(H.upload(ctx, spd), upper), dt)
+            _close(got, want, dt, f"cholesky-blocked/{dt}/{bshape}/{n}/upper={upper}")
+            other = np.triu(got, 1) if not upper else np.tril(got, -1)
+            assert np.abs(other).max() == 0.0
+        monkeypatch.setenv("NX_CUDA_CHOLESKY_BLOCKED", "0")
+        one_cta = _dev_wide(oracle, B.cholesky(H.upload(ctx, spd), False), dt)
+        monkeypatch.delenv("NX_CUDA_CHOLESKY_BLOCKED")
+        _close(_dev_wide(oracle, B.cholesky(H.upload(ctx, spd), False), dt), one_cta, dt, f"blocked vs one-CTA/{dt}/{n}")
+    n = 2048
+    a = rng.standard_normal((n, n))
+    spd = (a @ a.T / n + np.eye(n)).astype(npdt)
+    L = H.download(B.cholesky(H.upload(ctx, H.HostView.from_array(spd, dt)))).astype(np.float64)
+    assert np.abs(L @ L.T - spd).max() <= (2e-5 if dt == "f32" else 1e-12) * np.abs(spd).max()
+    # a matrix that stops being positive definite in a late panel is reported like a small one
+    bad = spd.copy()
+    bad[1500, 1500] = -1.0
+    with pytest.raises(Failure, match="cholesky: matrix is not positive definite"):
+        B.cholesky(H.upload(ctx, H.HostView.from_array(bad, dt)))
