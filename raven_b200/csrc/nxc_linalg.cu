@@ -242,6 +242,53 @@ nxc_trsm_kernel(const T *aw, T *xw, int64_t n, int64_t nrhs, int upper, int tran
   }
 }
 
+// ---- blocked triangular solve for large real systems ---------------------------------------------
+// Same panel shape as the blocked cholesky: M = op(A) is walked in NXC_CH_NB-row blocks in
+// substitution order; a block of X is solved against the diagonal block of M held in shared memory,
+// one thread per right-hand-side column (coalesced along X's rows), and the rows not yet solved lose
+// their coupling to the block through one product: X[rest] -= M[rest, blk] X[blk].  M is addressed
+// through its row / column strides, so `transpose` is a stride swap (real dtypes only).
+template <class T>
+__global__ void __launch_bounds__(128)
+nxc_trsm_diag_kernel(const T *aw, T *xw, int64_t n, int64_t nrhs, int64_t mrs, int64_t mcs, int64_t j0, int nb,
+                     int forward, int unit, int *status) {
+  __shared__ T S[NXC_CH_NB][NXC_CH_NB + 1];
+  const T *M = aw + (int64_t)blockIdx.y * n * n;
+  for (int e = threadIdx.x; e < NXC_CH_NB * NXC_CH_NB; e += blockDim.x) {
+    const int i = e / NXC_CH_NB, c = e % NXC_CH_NB;
+    // a ragged block is padded with the identity: the padded unknowns stay zero
+    S[i][c] = (i < nb && c < nb) ? M[(j0 + i) * mrs + (j0 + c) * mcs] : (T)(i == c ? 1 : 0);
+  }
+  __syncthreads();
+  if (!unit && blockIdx.x == 0 && threadIdx.x < nb && S[threadIdx.x][threadIdx.x] == (T)0) atomicExch(status, 2);
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nrhs) return;
+  T *X = xw + (int64_t)blockIdx.y * n * nrhs + j0 * nrhs + col;
+  T x[NXC_CH_NB];
+#pragma unroll
+  for (int c = 0; c < NXC_CH_NB; c++) x[c] = c < nb ? X[(int64_t)c * nrhs] : (T)0;
+  if (forward) {
+#pragma unroll
+    for (int c = 0; c < NXC_CH_NB; c++) {
+      T v = x[c];
+#pragma unroll
+      for (int k = 0; k < c; k++) v -= S[c][k] * x[k];
+      x[c] = unit ? v : v / S[c][c];
+    }
+  } else {
+#pragma unroll
+    for (int c = NXC_CH_NB - 1; c >= 0; c--) {
+      T v = x[c];
+#pragma unroll
+      for (int k = c + 1; k < NXC_CH_NB; k++) v -= S[c][k] * x[k];
+      x[c] = unit ? v : v / S[c][c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NXC_CH_NB; c++)
+    if (c < nb) X[(int64_t)c * nrhs] = x[c];
+}
+
 // ---- Householder QR on an m x n work matrix; Q (m x nq) formed from the reflectors ----------------
 template <class T>
 __global__ void __launch_bounds__(NXC_LA_THREADS)
@@ -309,6 +356,94 @@ nxc_qr_kernel(T *work, T *qbuf, T *taubuf, int64_t m, int64_t n, int64_t nq) {
   }
 }
 
+
+// ---- blocked Householder QR for large real matrices (compact WY) ---------------------------------
+// The one-CTA kernel above applies each reflector to the whole matrix with one thread per column:
+// 72 ms for one 512 x 512 matrix.  Large real matrices are factored in panels of NXC_QR_NB columns:
+// one CTA per matrix factors the panel with the same reflector arithmetic (LAPACK pivot sign,
+// tau = 0 for an already-reduced column) -- threads laid out as 32 panel columns x 16 row lanes, so
+// a warp reads one 128-byte panel row -- and accumulates the triangular factor T of the block
+// reflector H_0 ... H_{nb-1} = I - V T V^T in the same pass that applies H_j (the dot products
+// V[:, c]^T v_j for c < j are the T column, for c > j the update).  The panel's explicit V (unit
+// lower trapezoid) goes to its own buffer, and everything right of the panel -- and all of Q,
+// panels in reverse -- is three products through nxc_matmul: X -= V (T' (V^T X)).
+#define NXC_QR_NB 32
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_qr_panel_kernel(T *work, T *vall, T *tall, int64_t m, int64_t n, int64_t k, int64_t j0, int nb, int64_t npanels) {
+  constexpr int LANES = NXC_LA_THREADS / NXC_QR_NB;
+  __shared__ T sT[NXC_QR_NB][NXC_QR_NB + 1];
+  __shared__ T sw[LANES][NXC_QR_NB];
+  __shared__ T wv[NXC_QR_NB];
+  __shared__ T red[NXC_LA_THREADS / 32];
+  T *A = work + (int64_t)blockIdx.x * m * n;
+  T *V = vall + (int64_t)blockIdx.x * m * k;
+  T *Tm = tall + ((int64_t)blockIdx.x * npanels + j0 / NXC_QR_NB) * NXC_QR_NB * NXC_QR_NB;
+  const int c = threadIdx.x % NXC_QR_NB, r = threadIdx.x / NXC_QR_NB;
+  for (int e = threadIdx.x; e < NXC_QR_NB * NXC_QR_NB; e += blockDim.x) sT[e / NXC_QR_NB][e % NXC_QR_NB] = (T)0;
+  __syncthreads();
+  for (int jj = 0; jj < nb; jj++) {
+    const int64_t j = j0 + jj;
+    T part = (T)0;
+    for (int64_t i = j + 1 + threadIdx.x; i < m; i += blockDim.x) part += A[i * n + j] * A[i * n + j];
+    const T xnorm2 = nxc_la_block_sum<T>(part, red);
+    const T alpha = A[j * n + j];
+    T tau = (T)0;
+    if (xnorm2 != (T)0) {  // uniform
+      const T anorm = sqrt(alpha * alpha + xnorm2);
+      const T beta = alpha >= (T)0 ? -anorm : anorm;
+      tau = (beta - alpha) / beta;
+      const T scal = alpha - beta;
+      __syncthreads();  // everyone has read alpha
+      for (int64_t i = j + 1 + threadIdx.x; i < m; i += blockDim.x) A[i * n + j] = A[i * n + j] / scal;
+      if (threadIdx.x == 0) A[j * n + j] = beta;
+    }
+    __syncthreads();
+    // w_c = V[j][c] + sum_{i > j} v_i A[i][c] over the panel's columns
+    T acc = (T)0;
+    if (c < nb && c != jj)
+      for (int64_t i = j + 1 + r; i < m; i += LANES) acc += A[i * n + j] * A[i * n + j0 + c];
+    sw[r][c] = acc;
+    __syncthreads();
+    if (threadIdx.x < nb) {
+      T w = A[j * n + j0 + threadIdx.x];
+      for (int q = 0; q < LANES; q++) w += sw[q][threadIdx.x];
+      wv[threadIdx.x] = w;
+    }
+    __syncthreads();
+    // T[0:jj, jj] = -tau T[0:jj, 0:jj] (V[:, 0:jj]^T v_jj),  T[jj][jj] = tau
+    if (threadIdx.x < jj) {
+      T sacc = (T)0;
+      for (int b = threadIdx.x; b < jj; b++) sacc += sT[threadIdx.x][b] * wv[b];
+      sT[threadIdx.x][jj] = -tau * sacc;
+    } else if (threadIdx.x == jj) {
+      sT[jj][jj] = tau;
+    }
+    // H_jj on the panel's remaining columns
+    if (tau != (T)0 && c > jj && c < nb) {
+      const T wc = tau * wv[c];
+      if (r == 0) A[j * n + j0 + c] -= wc;
+      for (int64_t i = j + 1 + r; i < m; i += LANES) A[i * n + j0 + c] -= wc * A[i * n + j];
+    }
+    __syncthreads();
+  }
+  // the explicit unit lower trapezoid and the triangular factor
+  for (int64_t i = j0 + r; i < m; i += LANES)
+    if (c < nb) V[i * k + j0 + c] = i < j0 + c ? (T)0 : (i == j0 + c ? (T)1 : A[i * n + j0 + c]);
+  for (int e = threadIdx.x; e < NXC_QR_NB * NXC_QR_NB; e += blockDim.x) Tm[e] = sT[e / NXC_QR_NB][e % NXC_QR_NB];
+}
+
+// Q starts as the identity's first nq columns; R keeps the upper trapezoid
+template <class T>
+__global__ void __launch_bounds__(256) nxc_qr_eye_kernel(T *q, int64_t m, int64_t nq) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m * nq) q[(int64_t)blockIdx.y * m * nq + e] = e / nq == e % nq ? (T)1 : (T)0;
+}
+template <class T>
+__global__ void __launch_bounds__(256) nxc_qr_triu_kernel(T *w, int64_t m, int64_t n) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m * n && e % n < e / n) w[(int64_t)blockIdx.y * m * n + e] = (T)0;
+}
 
 template <class T> struct La3Map;
 template <> struct La3Map<float> { typedef float E; };
@@ -477,6 +612,44 @@ extern "C" nxc_status nxc_cholesky(nxc_ctx *ctx, const nxc_tensor *out, const nx
   return nxc_la_fail(ctx, s);
 }
 
+// blocked substitution on the contiguous work matrices aw [batch..., n, n], xw [batch..., n, nrhs]
+template <class T>
+static nxc_status nxc_trsm_blocked(nxc_ctx *ctx, const nxc_tensor *aw, const nxc_tensor *xw, int64_t n, int64_t nrhs,
+                                   int64_t nbatch, int upper, int transpose, int unit, int *st) {
+  const int nd = aw->ndim;
+  const bool forward = (upper != 0) == (transpose != 0);
+  const int64_t mrs = transpose ? 1 : n, mcs = transpose ? n : 1;
+  const int64_t blocks = (n + NXC_CH_NB - 1) / NXC_CH_NB;
+  for (int64_t bi = 0; bi < blocks; bi++) {
+    const int64_t j0 = (forward ? bi : blocks - 1 - bi) * NXC_CH_NB;
+    const int nb = (int)(n - j0 < NXC_CH_NB ? n - j0 : NXC_CH_NB);
+    nxc_trsm_diag_kernel<T><<<dim3((unsigned)((nrhs + 127) / 128), (unsigned)nbatch), 128, 0, ctx->stream>>>(
+        (const T *)aw->data, (T *)xw->data, n, nrhs, mrs, mcs, j0, nb, forward, unit, st);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) return nxc_cuda_fail(ctx, cudaGetLastError(), "triangular_solve block");
+    const int64_t r0 = forward ? j0 + nb : 0, rest = forward ? n - j0 - nb : j0;
+    if (rest <= 0) continue;
+    nxc_tensor mv = *aw, xb = *xw, xr = *xw, prod;
+    void *pbuf = NULL;
+    mv.offset = r0 * mrs + j0 * mcs;  mv.shape[nd - 2] = rest;  mv.shape[nd - 1] = nb;
+    mv.strides[nd - 2] = mrs;  mv.strides[nd - 1] = mcs;
+    xb.offset = j0 * nrhs;  xb.shape[nd - 2] = nb;
+    xr.offset = r0 * nrhs;  xr.shape[nd - 2] = rest;
+    nxc_status s = nxc_la_work(ctx, xw, xw->dtype, rest, nrhs, &prod, &pbuf);
+    if (!s) s = nxc_matmul(ctx, &prod, &mv, &xb);
+    if (!s) s = nxc_map2(ctx, NXC_SUB, &xr, &xr, &prod);
+    if (pbuf) nxc_free(ctx, pbuf);
+    if (s) return s;
+  }
+  return NXC_OK;
+}
+
+static bool nxc_trsm_use_blocked(int cdt, int64_t n) {
+  if (cdt != NXC_F32 && cdt != NXC_F64) return false;
+  if (getenv("NX_CUDA_TRSM_BLOCKED")) return atoi(getenv("NX_CUDA_TRSM_BLOCKED")) != 0 && n > NXC_CH_NB;
+  return n >= 128;
+}
+
 extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, const nxc_tensor *a, const nxc_tensor *b,
                                            int flags) {
   NXC_TRACE(ctx, "nxc_triangular_solve");
@@ -507,7 +680,11 @@ extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, 
   if (!s) s = nxc_memset(ctx, st, 0, sizeof(int));
   if (!s) s = nxc_la_move(ctx, &aw, a);
   if (!s) s = nxc_la_move(ctx, &xw, b);
-  if (!s) {
+  if (!s && nxc_trsm_use_blocked(cdt, n)) {
+    s = cdt == NXC_F32
+            ? nxc_trsm_blocked<float>(ctx, &aw, &xw, n, nrhs, nbatch, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, st)
+            : nxc_trsm_blocked<double>(ctx, &aw, &xw, n, nrhs, nbatch, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1, st);
+  } else if (!s) {
     NXC_LA_DISPATCH(cdt, {
       nxc_trsm_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((const T *)abuf, (T *)xbuf, n, nrhs, flags & 1,
                                                                                (flags >> 1) & 1, (flags >> 2) & 1, st);
@@ -521,6 +698,79 @@ extern "C" nxc_status nxc_triangular_solve(nxc_ctx *ctx, const nxc_tensor *out, 
   if (xbuf) nxc_free(ctx, xbuf);
   if (st) nxc_free(ctx, st);
   return nxc_la_fail(ctx, s);
+}
+
+// X[j0:, x0:] -= V_p op(T_p) (V_p^T X[j0:, x0:]) on views; X is a contiguous [batch..., xr, xc] work matrix
+static nxc_status nxc_qr_apply_block(nxc_ctx *ctx, const nxc_tensor *x, int64_t xc, int64_t x0, const nxc_tensor *vall,
+                                     const nxc_tensor *tall, int64_t m, int64_t k, int64_t p, int64_t j0, int nb, bool t_transposed) {
+  const int nd = x->ndim;
+  const int64_t mp = m - j0, cols = xc - x0;
+  if (cols <= 0) return NXC_OK;
+  nxc_tensor vp = *vall, vpt, xv = *x, tp = *tall, w1, w2, prod;
+  void *b1 = NULL, *b2 = NULL, *b3 = NULL;
+  vp.offset = j0 * k + j0;  vp.shape[nd - 2] = mp;  vp.shape[nd - 1] = nb;
+  vpt = vp;  vpt.shape[nd - 2] = nb;  vpt.shape[nd - 1] = mp;  vpt.strides[nd - 2] = 1;  vpt.strides[nd - 1] = k;
+  xv.offset = j0 * xc + x0;  xv.shape[nd - 2] = mp;  xv.shape[nd - 1] = cols;
+  tp.offset = p * NXC_QR_NB * NXC_QR_NB;  tp.shape[nd - 2] = nb;  tp.shape[nd - 1] = nb;
+  tp.strides[nd - 2] = t_transposed ? 1 : NXC_QR_NB;  tp.strides[nd - 1] = t_transposed ? NXC_QR_NB : 1;
+  nxc_status s = nxc_la_work(ctx, x, x->dtype, nb, cols, &w1, &b1);
+  if (!s) s = nxc_la_work(ctx, x, x->dtype, nb, cols, &w2, &b2);
+  if (!s) s = nxc_la_work(ctx, x, x->dtype, mp, cols, &prod, &b3);
+  if (!s) s = nxc_matmul(ctx, &w1, &vpt, &xv);
+  if (!s) s = nxc_matmul(ctx, &w2, &tp, &w1);
+  if (!s) s = nxc_matmul(ctx, &prod, &vp, &w2);
+  if (!s) s = nxc_map2(ctx, NXC_SUB, &xv, &xv, &prod);
+  if (b1) nxc_free(ctx, b1);
+  if (b2) nxc_free(ctx, b2);
+  if (b3) nxc_free(ctx, b3);
+  return s;
+}
+
+// w [batch..., m, n] is factored in place (R in its upper trapezoid), qw [batch..., m, nq] receives Q
+template <class T>
+static nxc_status nxc_qr_blocked(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tensor *qw, int64_t m, int64_t n, int64_t nq,
+                                 int64_t nbatch) {
+  const int64_t k = m < n ? m : n;
+  const int64_t npanels = (k + NXC_QR_NB - 1) / NXC_QR_NB;
+  nxc_tensor vall, tall;
+  void *vbuf = NULL, *tbuf = NULL;
+  nxc_status s = nxc_la_work(ctx, w, w->dtype, m, k, &vall, &vbuf);
+  if (!s) s = nxc_la_work(ctx, w, w->dtype, npanels * NXC_QR_NB, NXC_QR_NB, &tall, &tbuf);
+  for (int64_t p = 0; p < npanels && !s; p++) {
+    const int64_t j0 = p * NXC_QR_NB;
+    const int nb = (int)(k - j0 < NXC_QR_NB ? k - j0 : NXC_QR_NB);
+    nxc_qr_panel_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)w->data, (T *)vbuf, (T *)tbuf, m, n, k, j0, nb,
+                                                                                 npanels);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr panel");
+    // H_{nb-1} ... H_0 = (I - V T V^T)^T on the columns right of the panel
+    if (!s) s = nxc_qr_apply_block(ctx, w, n, j0 + nb, &vall, &tall, m, k, p, j0, nb, true);
+  }
+  if (!s && nq > 0) {
+    nxc_qr_eye_kernel<T><<<dim3((unsigned)((m * nq + 255) / 256), (unsigned)nbatch), 256, 0, ctx->stream>>>((T *)qw->data, m, nq);
+    ctx->launches++;
+    // Q = H_0 ... H_{k-1} I: block reflectors last to first; rows and columns before j0 are still the identity's
+    for (int64_t p = npanels - 1; p >= 0 && !s; p--) {
+      const int64_t j0 = p * NXC_QR_NB;
+      const int nb = (int)(k - j0 < NXC_QR_NB ? k - j0 : NXC_QR_NB);
+      s = nxc_qr_apply_block(ctx, qw, nq, j0, &vall, &tall, m, k, p, j0, nb, false);
+    }
+  }
+  if (!s && n > 0) {
+    nxc_qr_triu_kernel<T><<<dim3((unsigned)((m * n + 255) / 256), (unsigned)nbatch), 256, 0, ctx->stream>>>((T *)w->data, m, n);
+    ctx->launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr");
+  }
+  if (vbuf) nxc_free(ctx, vbuf);
+  if (tbuf) nxc_free(ctx, tbuf);
+  return s;
+}
+
+static bool nxc_qr_use_blocked(int cdt, int64_t m, int64_t n) {
+  if (cdt != NXC_F32 && cdt != NXC_F64) return false;
+  const int64_t k = m < n ? m : n;
+  if (getenv("NX_CUDA_QR_BLOCKED")) return atoi(getenv("NX_CUDA_QR_BLOCKED")) != 0 && k > NXC_QR_NB;
+  return k >= 128;
 }
 
 extern "C" nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor *r, const nxc_tensor *in, int reduced) {
@@ -548,7 +798,9 @@ extern "C" nxc_status nxc_qr(nxc_ctx *ctx, const nxc_tensor *q, const nxc_tensor
   s = nxc_la_work(ctx, in, cdt, m, nq, &qw, &qbuf);
   if (!s) s = nxc_alloc(ctx, (size_t)nbatch * (size_t)(k > 0 ? k : 1) * (size_t)nxc_elem_size(cdt), &tbuf);
   if (!s && n > 0) s = nxc_la_move(ctx, &w, in);
-  if (!s) {
+  if (!s && nxc_qr_use_blocked(cdt, m, n)) {
+    s = cdt == NXC_F32 ? nxc_qr_blocked<float>(ctx, &w, &qw, m, n, nq, nbatch) : nxc_qr_blocked<double>(ctx, &w, &qw, m, n, nq, nbatch);
+  } else if (!s) {
     NXC_LA_DISPATCH(cdt, { nxc_qr_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)wbuf, (T *)qbuf, (T *)tbuf, m, n, nq); })
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr");

@@ -159,3 +159,69 @@ def test_cholesky_blocked_large(ctx, oracle, dt, monkeypatch):
     bad[1500, 1500] = -1.0
     with pytest.raises(Failure, match="cholesky: matrix is not positive definite"):
         B.cholesky(H.upload(ctx, H.HostView.from_array(bad, dt)))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_triangular_solve_blocked_large(ctx, oracle, dt):
+    """n >= 128 real systems take the panel-blocked substitution (nxc_trsm_blocked): every flag
+    combination against the oracle at a ragged size, matrix / single-column right-hand sides,
+    batched, and the singular report from a late block."""
+    rng = np.random.default_rng(46)
+    npdt = np.float32 if dt == "f32" else np.float64
+    for bshape, n, nrhs in (((), 200, 70), ((2,), 256, 1), ((), 130, 300)):
+        a = rng.standard_normal(bshape + (n, n))
+        tri = {False: hv_of((np.tril(a) / n + np.eye(n)).astype(npdt), dt), True: hv_of((np.triu(a) / n + np.eye(n)).astype(npdt), dt)}
+        b = hv_of(rng.standard_normal(bshape + (n, nrhs)).astype(npdt), dt)
+        for upper in (False, True):
+            for tr in (False, True):
+                for unit in (False, True):
+                    want = _wide(oracle, oracle.triangular_solve(tri[upper], b, upper, tr, unit))
+                    got = _dev_wide(oracle, B.triangular_solve(H.upload(ctx, tri[upper]), H.upload(ctx, b), upper, tr, unit), dt)
+                    _close(got, want, dt, f"trsm-blocked/{dt}/{bshape}/{n}/{nrhs}/{upper}{tr}{unit}", scale=4)
+    n = 300
+    sing = np.tril(rng.standard_normal((n, n))) / n + np.eye(n)
+    sing[250, 250] = 0.0
+    rhs = H.upload(ctx, H.HostView.from_array(np.ones((n, 2), dtype=npdt), dt))
+    with pytest.raises(Failure, match="triangular_solve: triangular matrix is singular"):
+        B.triangular_solve(H.upload(ctx, H.HostView.from_array(sing.astype(npdt), dt)), rhs)
+    # the other triangle is never read
+    junk = sing.copy()
+    junk[250, 250] = 1.0
+    clean = H.download(B.triangular_solve(H.upload(ctx, H.HostView.from_array(junk.astype(npdt), dt)), rhs))
+    junk += np.triu(np.full((n, n), np.nan), 1)
+    assert np.array_equal(H.download(B.triangular_solve(H.upload(ctx, H.HostView.from_array(junk.astype(npdt), dt)), rhs)), clean)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_qr_blocked_large(ctx, oracle, dt, monkeypatch):
+    """min(m, n) >= 128 real matrices take the compact-WY blocked path (nxc_qr_blocked): against the
+    oracle (same reflector sign convention, so Q and R compare directly) for tall / wide / square /
+    ragged shapes, reduced and full, batched; against the one-CTA kernel; residuals at 1024."""
+    rng = np.random.default_rng(47)
+    npdt = np.float32 if dt == "f32" else np.float64
+    for bshape, m, n in (((), 200, 200), ((2,), 300, 150), ((), 140, 260), ((), 257, 129)):
+        x = hv_of(rng.standard_normal(bshape + (m, n)).astype(npdt), dt)
+        for red in (True, False):
+            wq, wr = oracle.qr(x, red)
+            gq, gr = B.qr(H.upload(ctx, x), red)
+            _close(_dev_wide(oracle, gq, dt), _wide(oracle, wq), dt, f"qr-blocked.Q/{dt}/{bshape}/{m}x{n}/{red}", scale=8)
+            _close(_dev_wide(oracle, gr, dt), _wide(oracle, wr), dt, f"qr-blocked.R/{dt}/{bshape}/{m}x{n}/{red}", scale=8)
+            r = _dev_wide(oracle, gr, dt)
+            assert np.abs(np.tril(r.reshape((-1,) + r.shape[-2:])[0], -1)).max() == 0.0
+    # a column that is already reduced (tau = 0) inside a panel, and a rank-deficient block
+    z = rng.standard_normal((200, 160)).astype(npdt)
+    z[41:, 40] = 0.0
+    z[:, 100:110] = 0.0
+    x = hv_of(z, dt)
+    wq, wr = oracle.qr(x, True)
+    gq, gr = B.qr(H.upload(ctx, x), True)
+    q, r = _dev_wide(oracle, gq, dt), _dev_wide(oracle, gr, dt)
+    tol = 2e-4 if dt == "f32" else 1e-11
+    assert np.abs(q @ r - z).max() <= tol * 10 and np.abs(q.T @ q - np.eye(160)).max() <= tol * 10
+    _close(r, _wide(oracle, wr), dt, f"qr-blocked.R/reduced columns/{dt}", scale=8)
+    m = 1024
+    a = rng.standard_normal((m, m)).astype(npdt)
+    q, r = B.qr(H.upload(ctx, H.HostView.from_array(a, dt)), True)
+    q, r = H.download(q).astype(np.float64), H.download(r).astype(np.float64)
+    assert np.abs(q @ r - a).max() <= tol * 40
+    assert np.abs(q.T @ q - np.eye(m)).max() <= tol * 40

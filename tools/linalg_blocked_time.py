@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Cholesky of single large real matrices on one B200: the panel-blocked path
+"""Cholesky (and qr / triangular_solve with n right-hand sides) of large real matrices on one B200: the panel-blocked path
 (nxc_linalg.cu, nxc_cholesky_blocked) against the one-CTA-per-matrix kernel it replaces there
 (NX_CUDA_CHOLESKY_BLOCKED=0) and against the host LAPACK numpy links (the reference's CPU backend
 calls its own unblocked loops; numpy's time is the stronger CPU bar). Host-synchronised wall time,
@@ -46,6 +46,14 @@ for dt in ("f32", "f64"):
             r[name] = t(lambda: B.cholesky(ts))
         os.environ.pop("NX_CUDA_CHOLESKY_BLOCKED")
         r["default_ms"] = t(lambda: B.cholesky(ts))
+        if batch == 1 or n <= 256:
+            ta = B.reshape(B.from_host(ctx, a.reshape(-1)), [batch, n, n])
+            for op, fn, var in (("qr", lambda: B.qr(ta), "NX_CUDA_QR_BLOCKED"), ("trsm", lambda: B.triangular_solve(ts, ta), "NX_CUDA_TRSM_BLOCKED")):
+                r[op + "_blocked_ms"] = t(fn)
+                if n <= 512:
+                    os.environ[var] = "0"
+                    r[op + "_one_cta_ms"] = t(fn)
+                    os.environ.pop(var)
         t0 = time.perf_counter()
         np.linalg.cholesky(spd)
         r["numpy_lapack_ms"] = round((time.perf_counter() - t0) * 1e3, 3)
