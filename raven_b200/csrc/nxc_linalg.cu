@@ -21,6 +21,7 @@
 // A device status word reports numeric failure; the host reads it (one 4-byte read-back) because
 // the reference raises synchronously. Large single matrices want the blocked, GEMM-fed variant;
 // this one is sized for the batched small/medium factorizations ML code issues.
+#include <cooperative_groups.h>
 #include "nxc_ops.cuh"
 
 #define NXC_LA_THREADS 512
@@ -433,6 +434,113 @@ nxc_qr_panel_kernel(T *work, T *vall, T *tall, int64_t m, int64_t n, int64_t k, 
   for (int e = threadIdx.x; e < NXC_QR_NB * NXC_QR_NB; e += blockDim.x) Tm[e] = sT[e / NXC_QR_NB][e % NXC_QR_NB];
 }
 
+// The same panel on a thread-block CLUSTER: the single CTA above walks an m x 32 panel through L2
+// three times per column (1.0 ms per panel at m = 4096).  Eight CTAs of a cluster each keep m / 8
+// panel rows in shared memory for the whole panel; the two reductions a column needs (the norm of
+// its tail, then the 32 dot products against v_j) are finished by every CTA writing its partial into
+// every peer's shared memory (DSMEM) and one cluster barrier -- each CTA then adds the eight partials
+// in rank order, so all of them derive the same tau / T and no value is ever broadcast back.
+#define NXC_QR_CS 8
+#define NXC_QR_PANEL_SMEM_MAX (200u * 1024u)
+template <class T>
+__global__ void __launch_bounds__(NXC_LA_THREADS)
+nxc_qr_panel_cluster_kernel(T *work, T *vall, T *tall, int64_t m, int64_t n, int64_t k, int64_t j0, int nb, int64_t npanels,
+                            int rpc) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int LANES = NXC_LA_THREADS / NXC_QR_NB, NB = NXC_QR_NB;
+  extern __shared__ __align__(16) unsigned char nxc_qr_smem[];
+  T *P = (T *)nxc_qr_smem;  // [rpc][NB]: this CTA's rows of the panel
+  __shared__ T sT[NB][NB + 1];
+  __shared__ T sw[LANES][NB];
+  __shared__ T wv[NB];
+  __shared__ T red[NXC_LA_THREADS / 32];
+  __shared__ T xn[NXC_QR_CS][2];   // per rank: partial tail norm; [owner][1] = the pivot
+  __shared__ T wpart[NXC_QR_CS][NB];
+  const int q = (int)cluster.block_rank();
+  const int64_t b = blockIdx.x / NXC_QR_CS;
+  T *A = work + b * m * n;
+  T *V = vall + b * m * k;
+  const int c = threadIdx.x % NB, r = threadIdx.x / NB;
+  const int64_t r_lo = j0 + (int64_t)q * rpc;
+  const int nloc = (int)(r_lo >= m ? 0 : (m - r_lo < rpc ? m - r_lo : rpc));
+  for (int e = threadIdx.x; e < nloc * NB; e += blockDim.x)
+    P[e] = (e % NB) < nb ? A[(r_lo + e / NB) * n + j0 + e % NB] : (T)0;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) sT[e / NB][e % NB] = (T)0;
+  __syncthreads();
+  cluster.sync();  // every peer is resident before its shared memory is written
+  for (int jj = 0; jj < nb; jj++) {
+    const int64_t j = j0 + jj;
+    const int owner = (int)((j - j0) / rpc);  // the rank holding row j
+    const int jl = (int)(j - r_lo);           // row j's local index there
+    const int lo = (int)(j + 1 - r_lo < 0 ? 0 : (j + 1 - r_lo > nloc ? nloc : j + 1 - r_lo));
+    T part = (T)0;
+    for (int li = lo + threadIdx.x; li < nloc; li += blockDim.x) part += P[li * NB + jj] * P[li * NB + jj];
+    const T mine = nxc_la_block_sum<T>(part, red);
+    if (threadIdx.x < NXC_QR_CS) {
+      T *peer = cluster.map_shared_rank(&xn[0][0], threadIdx.x);
+      peer[q * 2] = mine;
+      if (q == owner) peer[q * 2 + 1] = P[jl * NB + jj];
+    }
+    cluster.sync();
+    T xnorm2 = (T)0;
+    for (int t = 0; t < NXC_QR_CS; t++) xnorm2 += xn[t][0];
+    const T alpha = xn[owner][1];
+    T tau = (T)0;
+    if (xnorm2 != (T)0) {  // uniform across the cluster
+      const T anorm = sqrt(alpha * alpha + xnorm2);
+      const T beta = alpha >= (T)0 ? -anorm : anorm;
+      tau = (beta - alpha) / beta;
+      const T scal = alpha - beta;
+      for (int li = lo + threadIdx.x; li < nloc; li += blockDim.x) P[li * NB + jj] = P[li * NB + jj] / scal;
+      if (q == owner && threadIdx.x == 0) P[jl * NB + jj] = beta;
+    }
+    __syncthreads();
+    T acc = (T)0;
+    if (c < nb && c != jj)
+      for (int li = lo + r; li < nloc; li += LANES) acc += P[li * NB + jj] * P[li * NB + c];
+    sw[r][c] = acc;
+    __syncthreads();
+    if (threadIdx.x < NB) {
+      T w = (q == owner && threadIdx.x < nb) ? P[jl * NB + threadIdx.x] : (T)0;
+      for (int t = 0; t < LANES; t++) w += sw[t][threadIdx.x];
+      for (int t = 0; t < NXC_QR_CS; t++) cluster.map_shared_rank(&wpart[0][0], t)[q * NB + threadIdx.x] = w;
+    }
+    cluster.sync();
+    if (threadIdx.x < NB) {
+      T w = (T)0;
+      for (int t = 0; t < NXC_QR_CS; t++) w += wpart[t][threadIdx.x];
+      wv[threadIdx.x] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < jj) {
+      T sacc = (T)0;
+      for (int bb = threadIdx.x; bb < jj; bb++) sacc += sT[threadIdx.x][bb] * wv[bb];
+      sT[threadIdx.x][jj] = -tau * sacc;
+    } else if (threadIdx.x == jj) {
+      sT[jj][jj] = tau;
+    }
+    if (tau != (T)0 && c > jj && c < nb) {
+      const T wc = tau * wv[c];
+      if (q == owner && r == 0) P[jl * NB + c] -= wc;
+      for (int li = lo + r; li < nloc; li += LANES) P[li * NB + c] -= wc * P[li * NB + jj];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nloc * NB; e += blockDim.x) {
+    const int64_t i = r_lo + e / NB;
+    const int cc = e % NB;
+    if (cc < nb) {
+      A[i * n + j0 + cc] = P[e];
+      V[i * k + j0 + cc] = i < j0 + cc ? (T)0 : (i == j0 + cc ? (T)1 : P[e]);
+    }
+  }
+  if (q == 0) {
+    T *Tm = tall + (b * npanels + j0 / NB) * NB * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Tm[e] = sT[e / NB][e % NB];
+  }
+}
+
 // Q starts as the identity's first nq columns; R keeps the upper trapezoid
 template <class T>
 __global__ void __launch_bounds__(256) nxc_qr_eye_kernel(T *q, int64_t m, int64_t nq) {
@@ -736,13 +844,43 @@ static nxc_status nxc_qr_blocked(nxc_ctx *ctx, const nxc_tensor *w, const nxc_te
   void *vbuf = NULL, *tbuf = NULL;
   nxc_status s = nxc_la_work(ctx, w, w->dtype, m, k, &vall, &vbuf);
   if (!s) s = nxc_la_work(ctx, w, w->dtype, npanels * NXC_QR_NB, NXC_QR_NB, &tall, &tbuf);
+  // panels whose rows fit the cluster's shared memory (m - j0 <= 12800 f32 / 6400 f64) run there
+  const bool use_cluster = !(getenv("NX_CUDA_QR_CLUSTER") && atoi(getenv("NX_CUDA_QR_CLUSTER")) == 0);
+  const bool force_cluster = getenv("NX_CUDA_QR_CLUSTER") && atoi(getenv("NX_CUDA_QR_CLUSTER")) == 1;
+  static bool attr_set[2] = {false, false};
+  if (!s && use_cluster && !attr_set[sizeof(T) == 8]) {
+    cudaError_t e = cudaFuncSetAttribute(nxc_qr_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)NXC_QR_PANEL_SMEM_MAX);
+    if (e != cudaSuccess) s = nxc_cuda_fail(ctx, e, "qr panel attribute");
+    attr_set[sizeof(T) == 8] = true;
+  }
   for (int64_t p = 0; p < npanels && !s; p++) {
     const int64_t j0 = p * NXC_QR_NB;
     const int nb = (int)(k - j0 < NXC_QR_NB ? k - j0 : NXC_QR_NB);
-    nxc_qr_panel_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)w->data, (T *)vbuf, (T *)tbuf, m, n, k, j0, nb,
-                                                                                 npanels);
+    const int64_t rpc = (m - j0 + NXC_QR_CS - 1) / NXC_QR_CS;
+    const size_t panel_smem = (size_t)rpc * NXC_QR_NB * sizeof(T);
+    // a cluster per matrix pays when the panel is tall and the batch leaves SMs idle (256 x 128^2: 0.86 ms with
+    // one CTA per matrix, 3.5 ms with 2048 clustered CTAs)
+    if (use_cluster && panel_smem <= NXC_QR_PANEL_SMEM_MAX && (force_cluster || (nbatch * NXC_QR_CS <= 148 && m - j0 >= 512))) {
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = NXC_QR_CS;  attr[0].val.clusterDim.y = 1;  attr[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)(nbatch * NXC_QR_CS));
+      cfg.blockDim = dim3(NXC_LA_THREADS);
+      cfg.dynamicSmemBytes = panel_smem;
+      cfg.stream = ctx->stream;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, nxc_qr_panel_cluster_kernel<T>, (T *)w->data, (T *)vbuf, (T *)tbuf, m, n, k, j0, nb,
+                                         npanels, (int)rpc);
+      if (e != cudaSuccess) s = nxc_cuda_fail(ctx, e, "qr panel (cluster)");
+    } else {
+      nxc_qr_panel_kernel<T><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>((T *)w->data, (T *)vbuf, (T *)tbuf, m, n, k, j0,
+                                                                                   nb, npanels);
+    }
     ctx->launches++;
-    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr panel");
+    if (!s && cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "qr panel");
     // H_{nb-1} ... H_0 = (I - V T V^T)^T on the columns right of the panel
     if (!s) s = nxc_qr_apply_block(ctx, w, n, j0 + nb, &vall, &tall, m, k, p, j0, nb, true);
   }

@@ -208,6 +208,18 @@ def test_qr_blocked_large(ctx, oracle, dt, monkeypatch):
             _close(_dev_wide(oracle, gr, dt), _wide(oracle, wr), dt, f"qr-blocked.R/{dt}/{bshape}/{m}x{n}/{red}", scale=8)
             r = _dev_wide(oracle, gr, dt)
             assert np.abs(np.tril(r.reshape((-1,) + r.shape[-2:])[0], -1)).max() == 0.0
+    # both panel kernels (the cluster one is chosen for tall panels of small batches) against each other
+    x = hv_of(rng.standard_normal((2, 600, 200)).astype(npdt), dt)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NX_CUDA_QR_CLUSTER", mode)
+        gq, gr = B.qr(H.upload(ctx, x), True)
+        outs[mode] = (_dev_wide(oracle, gq, dt), _dev_wide(oracle, gr, dt))
+    monkeypatch.delenv("NX_CUDA_QR_CLUSTER")
+    _close(outs["1"][0], outs["0"][0], dt, f"qr cluster vs one-CTA panel Q/{dt}", scale=4)
+    _close(outs["1"][1], outs["0"][1], dt, f"qr cluster vs one-CTA panel R/{dt}", scale=4)
+    wq, wr = oracle.qr(x, True)
+    _close(outs["1"][1], _wide(oracle, wr), dt, f"qr cluster panel R vs oracle/{dt}", scale=8)
     # a column that is already reduced (tau = 0) inside a panel, and a rank-deficient block
     z = rng.standard_normal((200, 160)).astype(npdt)
     z[41:, 40] = 0.0
