@@ -564,7 +564,73 @@ __device__ __forceinline__ La3Thr nxc_la3_thr() {
   t.tid = (int)threadIdx.x; t.nt = (int)blockDim.x;
   t.lane = (int)(threadIdx.x & 31); t.lanes = 32;
   t.warp = (int)(threadIdx.x >> 5); t.nwarps = (int)(blockDim.x >> 5);
+  t.wide = 0;
   return t;
+}
+
+// The Jacobi kernels (eigh, svd) give a WARP a column pair and need a barrier per round-robin
+// step; one CTA has 16 warps for the n / 2 pairs of a step.  Launched as a thread-block cluster
+// (8 CTAs, 16 where the device schedules it) the team is 128 / 256 warps: all pairs of a 512-wide
+// matrix rotate at once, and the step barrier is the cluster's hardware barrier.  The working
+// matrices already live in global memory (L2); only the reduction scratch and the rotation counter
+// move from shared to global memory.
+__device__ __forceinline__ La3Thr nxc_la3_team(unsigned *rank, unsigned *size) {
+  unsigned r, n;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+  La3Thr t;
+  t.tid = (int)(r * blockDim.x + threadIdx.x); t.nt = (int)(n * blockDim.x);
+  t.lane = (int)(threadIdx.x & 31); t.lanes = 32;
+  t.warp = (int)(r * (blockDim.x >> 5) + (threadIdx.x >> 5)); t.nwarps = (int)(n * (blockDim.x >> 5));
+  t.wide = n > 1;
+  *rank = r; *size = n;
+  return t;
+}
+// per-matrix global scratch of a cluster team: NXC_LA_TEAM_RED doubles + 2 ints
+#define NXC_LA_TEAM_RED 256
+#define NXC_LA_TEAM_BYTES (NXC_LA_TEAM_RED * 8 + 64)
+
+// cluster width for `nbatch` matrices with `pairs` column pairs per step: 1 = plain launch
+template <class K>
+static int nxc_la_team_size(K kernel, int64_t nbatch, int64_t pairs) {
+  int cs = 1;
+  const char *env = getenv("NX_CUDA_LA_CLUSTER");
+  if (env) {
+    cs = atoi(env);
+    if (cs != 2 && cs != 4 && cs != 8 && cs != 16) cs = 1;
+  } else if (pairs >= 64) {
+    // widen while the batch leaves SMs free and a step still has a pair for every warp
+    while (cs < 16 && nbatch * cs * 2 <= 148 && pairs > (int64_t)cs * (NXC_LA_THREADS / 32)) cs *= 2;
+  }
+  if (cs == 16) {
+    // more than 8 CTAs per cluster is opt-in, and only where the device can place one
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(16); cfg.blockDim = dim3(NXC_LA_THREADS); cfg.attrs = attr; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      cs = 8;
+    }
+  }
+  return cs;
+}
+
+template <class K, class A>
+static cudaError_t nxc_la_team_launch(nxc_ctx *ctx, K kernel, int cs, int64_t nbatch, const A &args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(nbatch * cs));
+  cfg.blockDim = dim3(NXC_LA_THREADS);
+  cfg.stream = ctx->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args);
 }
 
 struct NxcEighArgs {
@@ -575,14 +641,19 @@ struct NxcEighArgs {
   int64_t n;
   int vectors;
   int *status;
+  char *team;  // NXC_LA_TEAM_BYTES per matrix when launched as clusters
 };
 
 template <class E>
-__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eigh_kernel(const __grid_constant__ NxcEighArgs a) {
-  __shared__ double red[NXC_LA_THREADS];
-  __shared__ int flags[2];
-  const int64_t b = blockIdx.x, nn = a.n * a.n;
-  la3_eigh_body<E>(nxc_la3_thr(), (const E *)a.a + b * nn, (E *)a.gt + b * nn, (E *)a.vt + b * nn, (E *)a.vo + b * nn,
+__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eigh_kernel(const NxcEighArgs a) {
+  __shared__ double sred[NXC_LA_THREADS / 32];
+  __shared__ int sflags[2];
+  unsigned rank, size;
+  const La3Thr t = nxc_la3_team(&rank, &size);
+  const int64_t b = blockIdx.x / size, nn = a.n * a.n;
+  double *red = t.wide ? (double *)(a.team + b * NXC_LA_TEAM_BYTES) : sred;
+  int *flags = t.wide ? (int *)(a.team + b * NXC_LA_TEAM_BYTES + NXC_LA_TEAM_RED * 8) : sflags;
+  la3_eigh_body<E>(t, (const E *)a.a + b * nn, (E *)a.gt + b * nn, (E *)a.vt + b * nn, (E *)a.vo + b * nn,
                    a.w + b * a.n, a.sg + b * a.n, a.rk + b * a.n, red, flags, a.n, a.vectors, 60, a.status);
 }
 
@@ -989,7 +1060,7 @@ extern "C" nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tens
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_a = carve(nb * nn * esz), o_gt = carve(nb * nn * esz), o_vt = carve(nb * nn * esz);
   const size_t o_vo = carve(vectors ? nb * nn * esz : 16), o_w = carve(nb * n * 8), o_sg = carve(nb * n * 8);
-  const size_t o_rk = carve(nb * n * 4), o_st = carve(sizeof(int));
+  const size_t o_rk = carve(nb * n * 4), o_st = carve(sizeof(int)), o_team = carve(nb * NXC_LA_TEAM_BYTES);
   char *base = NULL;
   if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
   s = nxc_memset(ctx, base + o_st, 0, sizeof(int));
@@ -1001,10 +1072,15 @@ extern "C" nxc_status nxc_eigh(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tens
     NxcEighArgs a;
     a.a = base + o_a; a.gt = base + o_gt; a.vt = base + o_vt; a.vo = base + o_vo;
     a.w = (double *)(base + o_w); a.sg = (double *)(base + o_sg); a.rk = (int *)(base + o_rk);
-    a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st);
-    NXC_LA_DISPATCH(cdt, { nxc_eigh_kernel<typename La3Map<T>::E><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a); })
+    a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st); a.team = base + o_team;
+    cudaError_t le = cudaSuccess;
+    NXC_LA_DISPATCH(cdt, {
+      auto kernel = nxc_eigh_kernel<typename La3Map<T>::E>;
+      le = nxc_la_team_launch(ctx, kernel, nxc_la_team_size(kernel, nbatch, (n + 1) / 2), nbatch, a);
+    })
     ctx->launches++;
-    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "eigh");
+    if (le != cudaSuccess) s = nxc_cuda_fail(ctx, le, "eigh");
+    else if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "eigh");
   }
   if (!s) {
     int h = 0;
@@ -1037,16 +1113,21 @@ struct NxcSvdArgs {
   Cd *coef;
   int64_t m, n, ucols, vrows;
   int *status;
+  char *team;  // NXC_LA_TEAM_BYTES per matrix when launched as clusters
 };
 
 template <class E>
-__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_svd_kernel(const __grid_constant__ NxcSvdArgs a) {
-  __shared__ double red[NXC_LA_THREADS];
-  __shared__ int flags[2];
-  const int64_t b = blockIdx.x;
+__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_svd_kernel(const NxcSvdArgs a) {
+  __shared__ double sred[NXC_LA_THREADS / 32];
+  __shared__ int sflags[2];
+  unsigned rank, size;
+  const La3Thr t = nxc_la3_team(&rank, &size);
+  const int64_t b = blockIdx.x / size;
+  double *red = t.wide ? (double *)(a.team + b * NXC_LA_TEAM_BYTES) : sred;
+  int *flags = t.wide ? (int *)(a.team + b * NXC_LA_TEAM_BYTES + NXC_LA_TEAM_RED * 8) : sflags;
   const bool tall = a.m >= a.n;
   const int64_t pr = tall ? a.m : a.n, pc = tall ? a.n : a.m, ncu = tall ? a.ucols : a.vrows;
-  la3_svd_body<E>(nxc_la3_thr(), (E *)a.gt + b * pc * pr, (E *)a.wt + b * pc * pc, (E *)a.ut + b * ncu * pr,
+  la3_svd_body<E>(t, (E *)a.gt + b * pc * pr, (E *)a.wt + b * pc * pc, (E *)a.ut + b * ncu * pr,
                   (E *)a.uo + b * a.m * a.ucols, (E *)a.vho + b * a.vrows * a.n, a.sig + b * pc, a.sg + b * pc, a.rk + b * pc,
                   a.rown + b * pr, a.coef + b * pr, red, flags, a.m, a.n, a.ucols, a.vrows, 60, a.status);
 }
@@ -1126,7 +1207,7 @@ extern "C" nxc_status nxc_svd(nxc_ctx *ctx, const nxc_tensor *u, const nxc_tenso
   const size_t o_gt = carve(nb * pc * pr * esz), o_wt = carve(nb * pc * pc * esz), o_ut = carve(nb * ncu * pr * esz);
   const size_t o_uo = carve(nb * m * ucols * esz), o_vho = carve(nb * vrows * n * esz), o_coef = carve(nb * pr * sizeof(Cd));
   const size_t o_sig = carve(nb * pc * 8), o_sg = carve(nb * pc * 8), o_rown = carve(nb * pr * 8), o_rk = carve(nb * pc * 4);
-  const size_t o_st = carve(sizeof(int));
+  const size_t o_st = carve(sizeof(int)), o_team = carve(nb * NXC_LA_TEAM_BYTES);
   char *base = NULL;
   if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
   s = nxc_memset(ctx, base + o_st, 0, sizeof(int));
@@ -1144,10 +1225,15 @@ extern "C" nxc_status nxc_svd(nxc_ctx *ctx, const nxc_tensor *u, const nxc_tenso
     a.gt = base + o_gt; a.wt = base + o_wt; a.ut = base + o_ut; a.uo = base + o_uo; a.vho = base + o_vho;
     a.sig = (double *)(base + o_sig); a.sg = (double *)(base + o_sg); a.rown = (double *)(base + o_rown);
     a.rk = (int *)(base + o_rk); a.coef = (Cd *)(base + o_coef);
-    a.m = m; a.n = n; a.ucols = ucols; a.vrows = vrows; a.status = (int *)(base + o_st);
-    NXC_LA_DISPATCH(cdt, { nxc_svd_kernel<typename La3Map<T>::E><<<(unsigned)nbatch, NXC_LA_THREADS, 0, ctx->stream>>>(a); })
+    a.m = m; a.n = n; a.ucols = ucols; a.vrows = vrows; a.status = (int *)(base + o_st); a.team = base + o_team;
+    cudaError_t le = cudaSuccess;
+    NXC_LA_DISPATCH(cdt, {
+      auto kernel = nxc_svd_kernel<typename La3Map<T>::E>;
+      le = nxc_la_team_launch(ctx, kernel, nxc_la_team_size(kernel, nbatch, (k + 1) / 2), nbatch, a);
+    })
     ctx->launches++;
-    if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "svd");
+    if (le != cudaSuccess) s = nxc_cuda_fail(ctx, le, "svd");
+    else if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "svd");
   }
   if (!s) s = nxc_la_status3(ctx, (int *)(base + o_st));
   if (!s) {

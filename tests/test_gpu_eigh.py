@@ -58,3 +58,28 @@ def test_eigh_errors(ctx):
         B.eigh(up(np.ones((2, 3)), "f64"))
     with pytest.raises(InvalidArgument, match="eigvalsh: linalg requires a float or complex dtype"):
         B.eigvalsh(up(np.ones((2, 2), dtype=np.int32), "i32"))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "c64"])
+def test_eigh_cluster_teams(ctx, dt, monkeypatch):
+    """Matrices with >= 64 column pairs per step are rotated by a thread-block cluster (nxc_linalg.cu,
+    nxc_la3_team): every team width gives the decomposition the one-CTA launch gives (same
+    schedule, same arithmetic per pair, so eigenvalues agree to rounding), batched as well."""
+    rng = np.random.default_rng(54)
+    n = 200
+    a = rng.standard_normal((2, n, n)) + (1j * rng.standard_normal((2, n, n)) if dt == "c64" else 0)
+    h = a + np.conj(np.swapaxes(a, -1, -2))
+    npdt = {"f32": np.float32, "f64": np.float64, "c64": np.complex128}[dt]
+    hv = H.HostView.from_array(h.astype(npdt), dt)
+    want = np.linalg.eigvalsh(h)
+    tol = 2e-5 if dt == "f32" else 1e-11
+    for width in ("1", "2", "8", "16", None):
+        if width is None:
+            monkeypatch.delenv("NX_CUDA_LA_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("NX_CUDA_LA_CLUSTER", width)
+        w, v = B.eigh(H.upload(ctx, hv))
+        w, v = H.download(w), H.download(v).astype(np.complex128 if dt == "c64" else np.float64)
+        assert np.abs(w - want).max() <= tol * np.abs(want).max(), width
+        assert np.abs(h @ v - v * w[:, None, :]).max() <= 20 * tol * np.abs(want).max(), width
+        assert np.abs(np.conj(np.swapaxes(v, -1, -2)) @ v - np.eye(n)).max() <= 20 * tol, width

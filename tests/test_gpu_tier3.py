@@ -113,3 +113,31 @@ def test_eig_balances_badly_scaled_input(ctx, oracle):
     want = np.linalg.eigvals(a)
     assert eig_set_err(w, want) <= 1e-12 * np.abs(want).max()
     assert eig_set_err(oracle.eig(hv, False).numpy(), want) <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_svd_cluster_teams(ctx, dt, monkeypatch):
+    """The svd's Jacobi sweeps on a thread-block cluster (nxc_linalg.cu, nxc_la3_team): every team
+    width reproduces numpy's singular values and a valid factorisation, tall, wide and rank-deficient
+    (the Gram-Schmidt completion also runs across the cluster)."""
+    rng = np.random.default_rng(61)
+    npdt = np.float32 if dt == "f32" else np.float64
+    tol = 3e-5 if dt == "f32" else 1e-11
+    cases = {"tall": rng.standard_normal((260, 180)), "wide": rng.standard_normal((2, 150, 230))}
+    low = rng.standard_normal((200, 140))
+    low[:, 100:] = 0.0
+    cases["rank-deficient"] = low
+    for name, a in cases.items():
+        a = a.astype(npdt)
+        want = np.linalg.svd(a.astype(np.float64), compute_uv=False)
+        for width in ("1", "4", "16", None):
+            if width is None:
+                monkeypatch.delenv("NX_CUDA_LA_CLUSTER", raising=False)
+            else:
+                monkeypatch.setenv("NX_CUDA_LA_CLUSTER", width)
+            u, s, vh = B.svd(H.upload(ctx, H.HostView.from_array(a, dt)), True)
+            u, s, vh = (H.download(x).astype(np.float64) for x in (u, s, vh))
+            assert np.abs(s - want).max() <= tol * want.max(), (name, width)
+            assert np.abs(u[..., :, : s.shape[-1]] @ (s[..., :, None] * vh[..., : s.shape[-1], :]) - a).max() <= 30 * tol * want.max(), (name, width)
+            assert np.abs(np.swapaxes(u, -1, -2) @ u - np.eye(u.shape[-1])).max() <= 30 * tol, (name, width)
+            assert np.abs(vh @ np.swapaxes(vh, -1, -2) - np.eye(vh.shape[-2])).max() <= 30 * tol, (name, width)
