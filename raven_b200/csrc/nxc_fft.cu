@@ -102,29 +102,32 @@ __device__ __forceinline__ double2 nxc_fft_read(const void *src, int kind, int64
   }
 }
 
+// element k of line L's transform input (line base `so` in source elements)
+__device__ __forceinline__ double2 nxc_fft_fetch(const NxcFftGather &g, int64_t so, int64_t k) {
+  double2 v = make_double2(0.0, 0.0);
+  if (k < g.n) {
+    if (k < g.n_src) {
+      v = nxc_fft_read(g.src, g.src_kind, so + k * g.stride);
+    } else if (g.hermitian) {
+      // conjugate mirror of bin n-k when that bin was supplied (reference: nx_c_fft.c:1014-1021)
+      const int64_t q = g.n - k;
+      if (q >= 1 && q < g.n_src && q != k) {
+        v = nxc_fft_read(g.src, g.src_kind, so + q * g.stride);
+        v.y = -v.y;
+      }
+    }
+    if (g.bluestein) v = cmul(v, chirp_at(g.sign, k, g.n));
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(256) nxc_fft_gather_kernel(const __grid_constant__ NxcFftGather g) {
   const int64_t total = g.n_lines * g.m;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t L = i / g.m, k = i - L * g.m;
-    double2 v = make_double2(0.0, 0.0);
-    if (k < g.n) {
-      int64_t so, dof;
-      nxc_fft_line_base(g.lines, L, so, dof);
-      if (!g.hermitian) {
-        if (k < g.n_src) v = nxc_fft_read(g.src, g.src_kind, so + k * g.stride);
-      } else if (k < g.n_src) {
-        v = nxc_fft_read(g.src, g.src_kind, so + k * g.stride);
-      } else {
-        // conjugate mirror of bin n-k when that bin was supplied (reference: nx_c_fft.c:1014-1021)
-        const int64_t q = g.n - k;
-        if (q >= 1 && q < g.n_src && q != k) {
-          v = nxc_fft_read(g.src, g.src_kind, so + q * g.stride);
-          v.y = -v.y;
-        }
-      }
-      if (g.bluestein) v = cmul(v, chirp_at(g.sign, k, g.n));
-    }
-    g.work[i] = v;
+    int64_t so = 0, dof = 0;
+    if (k < g.n) nxc_fft_line_base(g.lines, L, so, dof);
+    g.work[i] = nxc_fft_fetch(g, so, k);
   }
 }
 
@@ -140,26 +143,30 @@ struct NxcFftScatter {
   int bluestein;
 };
 
+// output element k of a line (line base `dof` in destination elements)
+__device__ __forceinline__ void nxc_fft_put(const NxcFftScatter &g, int64_t dof, int64_t k, double2 v) {
+  if (g.bluestein) {
+    v = cmul(v, chirp_at(g.sign, k, g.n));
+    const double inv = 1.0 / (double)g.m;
+    v.x *= inv;
+    v.y *= inv;
+  }
+  const int64_t off = dof + k * g.stride;
+  switch (g.dst_kind) {
+    case NXC_FFT_SRC_C32: ((float2 *)g.dst)[off] = make_float2((float)v.x, (float)v.y); break;
+    case NXC_FFT_SRC_C64: ((double2 *)g.dst)[off] = v; break;
+    case NXC_FFT_SRC_F32: ((float *)g.dst)[off] = (float)v.x; break;
+    default: ((double *)g.dst)[off] = v.x; break;
+  }
+}
+
 __global__ void __launch_bounds__(256) nxc_fft_scatter_kernel(const __grid_constant__ NxcFftScatter g) {
   const int64_t total = g.n_lines * g.n_out;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t L = i / g.n_out, k = i - L * g.n_out;
-    double2 v = g.work[L * g.m + k];
-    if (g.bluestein) {
-      v = cmul(v, chirp_at(g.sign, k, g.n));
-      const double inv = 1.0 / (double)g.m;
-      v.x *= inv;
-      v.y *= inv;
-    }
     int64_t so, dof;
     nxc_fft_line_base(g.lines, L, so, dof);
-    const int64_t off = dof + k * g.stride;
-    switch (g.dst_kind) {
-      case NXC_FFT_SRC_C32: ((float2 *)g.dst)[off] = make_float2((float)v.x, (float)v.y); break;
-      case NXC_FFT_SRC_C64: ((double2 *)g.dst)[off] = v; break;
-      case NXC_FFT_SRC_F32: ((float *)g.dst)[off] = (float)v.x; break;
-      default: ((double *)g.dst)[off] = v.x; break;
-    }
+    nxc_fft_put(g, dof, k, g.work[L * g.m + k]);
   }
 }
 
@@ -167,27 +174,105 @@ __global__ void __launch_bounds__(256) nxc_fft_scatter_kernel(const __grid_const
 // Stockham radix-2, stage Ns = 1, 2, 4, ...: butterfly j (0 <= j < m/2) reads in[j], in[j + m/2],
 // twiddles the second by exp(sign*i*pi*(j mod Ns)/Ns), and writes a+b, a-b to
 // out[(j div Ns)*2Ns + j mod Ns] and Ns further: the output of the last stage is in natural order.
-__global__ void nxc_fft_smem_kernel(double2 *__restrict__ work, int64_t m, int log2m, int sign) {
-  extern __shared__ double2 fsm[];
-  double2 *a = fsm, *b = fsm + m;
-  double2 *line = work + (int64_t)blockIdx.x * m;
-  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) a[i] = line[i];
+//
+// Lines of m <= NXC_FFT_SMEM_MAX points never leave shared memory: a CTA takes `lpc` whole lines,
+// reads them STRAIGHT from the source tensor (FUSED: strided, converted, Hermitian-mirrored as the
+// gather kernel would) or from the work buffer, runs every stage between two ping-pong buffers and
+// writes the result straight to the destination -- the transform costs one read and one write of
+// the data.  Two radix-2 stages are taken per pass (a thread carries butterflies j and j + m/4 of
+// stage Ns through stage 2 Ns in registers: the same additions and multiplications in the same
+// order as two radix-2 passes, half the barriers and shared-memory traffic), and twiddles come
+// from a table tw[i] = exp(sign i pi i / (m/2)) computed once per pass with sincospi of the
+// reduced angle -- the value each butterfly used to recompute in double precision.
+// tw[Ns + k] = exp(sign i pi k / Ns) for Ns = 1, 2, 4, ..., m / 2 and k < Ns: every stage reads a
+// CONTIGUOUS run (one table indexed k * (m / 2 / Ns) made a warp touch 32 cache lines per load)
+__global__ void __launch_bounds__(256) nxc_fft_twiddle_kernel(double2 *tw, int64_t m, int sign) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i == 0) { tw[0] = make_double2(1.0, 0.0); continue; }
+    const int64_t Ns = (int64_t)1 << (63 - __clzll(i));
+    tw[i] = cispi(sign, i - Ns, Ns);
+  }
+}
+
+struct NxcFftCore {
+  double2 *work;        // !FUSED: n_lines contiguous lines, transformed in place
+  const double2 *tw;    // m twiddles, stage-major (nxc_fft_twiddle_kernel)
+  int sign;
+  int64_t n_lines;
+  int m, log2m, lpc;
+};
+
+template <bool FUSED>
+__global__ void nxc_fft_lines_kernel(const __grid_constant__ NxcFftCore c, const __grid_constant__ NxcFftGather g,
+                                     const __grid_constant__ NxcFftScatter sc) {
+  extern __shared__ __align__(16) unsigned char nxc_fft_smem[];
+  const int m = c.m, half = m >> 1, quarter = m >> 2;
+  double2 *a = (double2 *)nxc_fft_smem, *b = a + (size_t)c.lpc * m;
+  int64_t *base = (int64_t *)(b + (size_t)c.lpc * m);  // [lpc][2]: source / destination line bases
+  const int64_t L0 = (int64_t)blockIdx.x * c.lpc;
+  const int nl = (int)(c.n_lines - L0 < c.lpc ? c.n_lines - L0 : c.lpc);
+  if (FUSED) {
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) nxc_fft_line_base(g.lines, L0 + l, base[2 * l], base[2 * l + 1]);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nl * m; i += blockDim.x) {
+    const int l = i >> c.log2m, k = i & (m - 1);
+    a[i] = FUSED ? nxc_fft_fetch(g, base[2 * l], k) : c.work[(L0 + l) * m + k];
+  }
   __syncthreads();
-  const int64_t half = m >> 1;
-  for (int st = 0; st < log2m; st++) {
-    const int64_t Ns = (int64_t)1 << st;
-    for (int64_t j = threadIdx.x; j < half; j += blockDim.x) {
-      const int64_t k = j & (Ns - 1);
-      const double2 u0 = a[j];
-      const double2 u1 = cmul(a[j + half], cispi(sign, k, Ns));
-      const int64_t j0 = ((j - k) << 1) + k;
-      b[j0] = make_double2(u0.x + u1.x, u0.y + u1.y);
-      b[j0 + Ns] = make_double2(u0.x - u1.x, u0.y - u1.y);
+  int st = 0;
+  for (; st + 1 < c.log2m; st += 2) {
+    const int Ns = 1 << st;
+    for (int i = threadIdx.x; i < nl * quarter; i += blockDim.x) {
+      const int l = i >> (c.log2m - 2), j = i & (quarter - 1);
+      const double2 *x = a + (size_t)l * m;
+      double2 *y = b + (size_t)l * m;
+      const int k = j & (Ns - 1);
+      const double2 w1 = __ldg(c.tw + Ns + k);
+      const double2 w2a = __ldg(c.tw + 2 * Ns + k);
+      // exp(sign i pi (k + Ns) / 2Ns) = (sign i) w2a: a quarter turn, exact
+      const double2 w2b = c.sign < 0 ? make_double2(w2a.y, -w2a.x) : make_double2(-w2a.y, w2a.x);
+      // stage Ns: butterflies j and j + m/4
+      const double2 p0 = x[j], p1 = cmul(x[j + half], w1);
+      const double2 q0 = x[j + quarter], q1 = cmul(x[j + quarter + half], w1);
+      const double2 x0 = make_double2(p0.x + p1.x, p0.y + p1.y), x1 = make_double2(p0.x - p1.x, p0.y - p1.y);
+      const double2 y0 = make_double2(q0.x + q1.x, q0.y + q1.y), y1 = make_double2(q0.x - q1.x, q0.y - q1.y);
+      // stage 2 Ns: butterflies 2 (j - k) + k and Ns further
+      const double2 u = cmul(y0, w2a), v = cmul(y1, w2b);
+      const int o = ((j - k) << 2) + k;
+      y[o] = make_double2(x0.x + u.x, x0.y + u.y);
+      y[o + Ns] = make_double2(x1.x + v.x, x1.y + v.y);
+      y[o + 2 * Ns] = make_double2(x0.x - u.x, x0.y - u.y);
+      y[o + 3 * Ns] = make_double2(x1.x - v.x, x1.y - v.y);
     }
     __syncthreads();
     double2 *t = a; a = b; b = t;
   }
-  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) line[i] = a[i];
+  if (st < c.log2m) {  // odd log2 m: the last stage alone, Ns = m / 2
+    const int Ns = 1 << st;
+    for (int i = threadIdx.x; i < nl * half; i += blockDim.x) {
+      const int l = i >> (c.log2m - 1), j = i & (half - 1);
+      const double2 *x = a + (size_t)l * m;
+      double2 *y = b + (size_t)l * m;
+      const int k = j & (Ns - 1);
+      const double2 u0 = x[j];
+      const double2 u1 = cmul(x[j + half], __ldg(c.tw + Ns + k));
+      const int o = ((j - k) << 1) + k;
+      y[o] = make_double2(u0.x + u1.x, u0.y + u1.y);
+      y[o + Ns] = make_double2(u0.x - u1.x, u0.y - u1.y);
+    }
+    __syncthreads();
+    double2 *t = a; a = b; b = t;
+  }
+  if (FUSED) {
+    const int n_out = (int)sc.n_out;
+    for (int i = threadIdx.x; i < nl * n_out; i += blockDim.x) {
+      const int l = i / n_out, k = i - l * n_out;
+      nxc_fft_put(sc, base[2 * l + 1], k, a[(size_t)l * m + k]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nl * m; i += blockDim.x) c.work[L0 * m + i] = a[i];
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -236,27 +321,47 @@ static unsigned nxc_fft_grid(nxc_ctx *ctx, int64_t items) {
 
 // In-place transform of n_lines contiguous lines of power-of-two length m. `tmp` is a second
 // buffer of the same size (only used when m > NXC_FFT_SMEM_MAX).
+template <bool FUSED>
+static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, double2 *work, const NxcFftGather *g, const NxcFftScatter *sc,
+                                       int64_t n_lines, int64_t m, int sign) {
+  int log2m = 0;
+  while (((int64_t)1 << log2m) < m) log2m++;
+  double2 *tw = NULL;
+  nxc_status s = nxc_alloc(ctx, sizeof(double2) * (size_t)m, (void **)&tw);
+  if (s) return s;
+  nxc_fft_twiddle_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(tw, m, sign);
+  ctx->launches++;
+  NxcFftCore c;
+  c.work = work; c.tw = tw; c.sign = sign; c.n_lines = n_lines; c.m = (int)m; c.log2m = log2m;
+  // enough lines per CTA to give 256 threads a quarter-butterfly each; long lines get more threads
+  c.lpc = (int)(m >= 1024 ? 1 : 1024 / m);
+  if (c.lpc > n_lines) c.lpc = (int)n_lines;
+  const int threads = m <= 1024 ? 256 : (m == 2048 ? 512 : 1024);
+  const size_t smem = (size_t)c.lpc * (2 * (size_t)m * sizeof(double2) + 16);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[FUSED]) {
+    cudaError_t e = cudaFuncSetAttribute(nxc_fft_lines_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * NXC_FFT_SMEM_MAX * sizeof(double2) + 16));
+    if (e != cudaSuccess) { nxc_free(ctx, tw); return nxc_cuda_fail(ctx, e, "fft attribute"); }
+    attr_set[FUSED] = true;
+  }
+  NxcFftGather g0;
+  NxcFftScatter s0;
+  if (!FUSED) { memset(&g0, 0, sizeof g0); memset(&s0, 0, sizeof s0); g = &g0; sc = &s0; }
+  const int64_t ctas = (n_lines + c.lpc - 1) / c.lpc;
+  if (ctas > 0x7FFFFFFF) { nxc_free(ctx, tw); return NXC_ERR_SHAPE; }  // > 2^31 CTAs: beyond any device's memory
+  nxc_fft_lines_kernel<FUSED><<<(unsigned)ctas, threads, smem, ctx->stream>>>(c, *g, *sc);
+  ctx->launches++;
+  if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft lines");
+  nxc_free(ctx, tw);
+  return s;
+}
+
 static nxc_status nxc_fft_core(nxc_ctx *ctx, double2 *work, double2 *tmp, int64_t n_lines, int64_t m, int sign) {
   int log2m = 0;
   while (((int64_t)1 << log2m) < m) log2m++;
   if (log2m == 0) return NXC_OK;
-  if (m <= NXC_FFT_SMEM_MAX) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      NXC_CUDA_TRY(ctx, cudaFuncSetAttribute(nxc_fft_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             2 * NXC_FFT_SMEM_MAX * (int)sizeof(double2)));
-      attr_set = true;
-    }
-    int threads = (int)(m / 2);
-    if (threads < 32) threads = 32;
-    if (threads > 512) threads = 512;
-    for (int64_t l0 = 0; l0 < n_lines; l0 += 0x40000000) {  // grid.x limit
-      const int64_t nl = n_lines - l0 < 0x40000000 ? n_lines - l0 : 0x40000000;
-      nxc_fft_smem_kernel<<<(unsigned)nl, threads, 2 * m * sizeof(double2), ctx->stream>>>(work + l0 * m, m, log2m, sign);
-      NXC_LAUNCH_CHECK(ctx);
-    }
-    return NXC_OK;
-  }
+  if (m <= NXC_FFT_SMEM_MAX) return nxc_fft_lines_launch<false>(ctx, work, NULL, NULL, n_lines, m, sign);
   double2 *a = work, *b = tmp;
   for (int st = 0; st < log2m; st++) {
     nxc_fft_global_pass_kernel<<<nxc_fft_grid(ctx, n_lines * (m / 2)), 256, 0, ctx->stream>>>(a, b, n_lines, m, st, sign);
@@ -302,6 +407,24 @@ static nxc_status nxc_fft_pass(nxc_ctx *ctx, const NxcFftPass &p) {
   if (!pow2) {
     m = 1;
     while (m < 2 * p.n - 1) m <<= 1;
+  }
+  if (pow2 && m >= 2 && m <= NXC_FFT_SMEM_MAX) {
+    // one kernel: source tensor -> shared memory -> destination tensor
+    NxcFftGather g;
+    g.lines = ln;
+    g.src = (const char *)src->data + src->offset * nxc_fft_esize(p.src_kind);
+    g.work = NULL;
+    g.n_lines = n_lines; g.n = p.n; g.n_src = p.n_src; g.m = m;
+    g.stride = src->strides[p.axis];
+    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = 0; g.hermitian = p.hermitian;
+    NxcFftScatter sc;
+    sc.lines = ln;
+    sc.dst = (char *)dst->data + dst->offset * nxc_fft_esize(p.dst_kind);
+    sc.work = NULL;
+    sc.n_lines = n_lines; sc.n = p.n; sc.n_out = p.n_out; sc.m = m;
+    sc.stride = dst->strides[p.axis];
+    sc.dst_kind = p.dst_kind; sc.sign = p.sign; sc.bluestein = 0;
+    return nxc_fft_lines_launch<true>(ctx, NULL, &g, &sc, n_lines, m, p.sign);
   }
   const size_t wbytes = sizeof(double2) * (size_t)n_lines * (size_t)m;
   double2 *work = NULL, *tmp = NULL, *bf = NULL;
