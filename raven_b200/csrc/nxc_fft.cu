@@ -179,10 +179,8 @@ __global__ void __launch_bounds__(256) nxc_fft_scatter_kernel(const __grid_const
 // reads them STRAIGHT from the source tensor (FUSED: strided, converted, Hermitian-mirrored as the
 // gather kernel would) or from the work buffer, runs every stage between two ping-pong buffers and
 // writes the result straight to the destination -- the transform costs one read and one write of
-// the data.  Two radix-2 stages are taken per pass (a thread carries butterflies j and j + m/4 of
-// stage Ns through stage 2 Ns in registers: the same additions and multiplications in the same
-// order as two radix-2 passes, half the barriers and shared-memory traffic), and twiddles come
-// from a table tw[i] = exp(sign i pi i / (m/2)) computed once per pass with sincospi of the
+// the data.  Two radix-2 stages are taken per pass in registers (nxc_fft_stages: a 1024-point
+// line is 5 shared-memory round trips, not 10) between two ping-pong buffers, and twiddles come from a table computed once per call with sincospi of the
 // reduced angle -- the value each butterfly used to recompute in double precision.
 // tw[Ns + k] = exp(sign i pi k / Ns) for Ns = 1, 2, 4, ..., m / 2 and k < Ns: every stage reads a
 // CONTIGUOUS run (one table indexed k * (m / 2 / Ns) made a warp touch 32 cache lines per load)
@@ -200,13 +198,74 @@ struct NxcFftCore {
   int sign;
   int64_t n_lines;
   int m, log2m, lpc;
+  int npass, plan;      // stages taken by pass i = (plan >> 4 i) & 15
+  int swz;              // slot swizzle shift = stages of the first pass (>= 3)
 };
 
+// Shared-memory slot of element o of a line: the first pass makes thread j write the 2^R contiguous
+// elements 2^R j .., one per store instruction -- unswizzled, the threads of a quarter-warp would
+// land on one or two 16-byte bank groups (4-way conflicts for R = 2).  XOR with the bits above an
+// aligned group of 8 permutes slots inside that group, so the contiguous runs every other access
+// makes stay conflict-free too.
+__device__ __forceinline__ int nxc_fft_swz(int o, int sh) { return o ^ ((o >> sh) & 7); }
+
+// R radix-2 stages on the 2^R points x[j + t m / 2^R] held in registers: after r stages the points
+// form 2^r sets (set q continues at output offset q Ns with twiddle index k + q Ns), and stage r
+// turns set q into sets q (sums) and q + 2^r (differences) -- the arithmetic of R Stockham passes,
+// one shared-memory round trip.  Twiddles of the upper half of a stage's sets are the lower half's
+// turned by a quarter (exact), so a pass loads 2^(R-1) of them, each a contiguous run across threads.
+template <int R>
+__device__ __forceinline__ void nxc_fft_stages(double2 (&v)[1 << R], const double2 *__restrict__ tw, int k, int Ns, int sign) {
+  constexpr int N = 1 << R;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    double2 u[N], w[N / 2 > 0 ? N / 2 : 1];
+#pragma unroll
+    for (int q = 0; q < (1 << r); q++) {
+      if (r == 0 || q < (1 << (r - (r > 0)))) {
+        w[q] = __ldg(tw + (Ns << r) + k + q * Ns);
+      } else {
+        const double2 z = w[q - (1 << (r - (r > 0)))];
+        w[q] = sign < 0 ? make_double2(z.y, -z.x) : make_double2(-z.y, z.x);
+      }
+#pragma unroll
+      for (int t = 0; t < (N >> (r + 1)); t++) {
+        const double2 a = v[q + (t << r)];
+        const double2 b = cmul(v[q + (t << r) + (N >> 1)], w[q]);
+        u[q + (t << (r + 1))] = make_double2(a.x + b.x, a.y + b.y);
+        u[q + (1 << r) + (t << (r + 1))] = make_double2(a.x - b.x, a.y - b.y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = u[i];
+  }
+}
+
+// one pass over the CTA's lines, buffer `src` to buffer `dst`, a group of 2^R points at a time
+template <int R>
+__device__ __forceinline__ void nxc_fft_pass_r(const double2 *src, double2 *dst, const NxcFftCore &c, int nl, int st) {
+  constexpr int N = 1 << R;
+  const int groups = c.m >> R, Ns = 1 << st;
+  for (int i = threadIdx.x; i < nl * groups; i += blockDim.x) {
+    const int l = i >> (c.log2m - R), j = i & (groups - 1), k = j & (Ns - 1);
+    const double2 *x = src + (size_t)l * c.m;
+    double2 *y = dst + (size_t)l * c.m;
+    double2 v[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) v[t] = x[nxc_fft_swz(j + t * groups, c.swz)];
+    nxc_fft_stages<R>(v, c.tw, k, Ns, c.sign);
+    const int o = ((j - k) << R) + k;
+#pragma unroll
+    for (int q = 0; q < N; q++) y[nxc_fft_swz(o + q * Ns, c.swz)] = v[q];
+  }
+  __syncthreads();
+}
+
 template <bool FUSED>
-__global__ void nxc_fft_lines_kernel(const __grid_constant__ NxcFftCore c, const __grid_constant__ NxcFftGather g,
-                                     const __grid_constant__ NxcFftScatter sc) {
+__global__ void __launch_bounds__(1024) nxc_fft_lines_kernel(const __grid_constant__ NxcFftCore c, const __grid_constant__ NxcFftGather g,
+                                                            const __grid_constant__ NxcFftScatter sc) {
   extern __shared__ __align__(16) unsigned char nxc_fft_smem[];
-  const int m = c.m, half = m >> 1, quarter = m >> 2;
+  const int m = c.m;
   double2 *a = (double2 *)nxc_fft_smem, *b = a + (size_t)c.lpc * m;
   int64_t *base = (int64_t *)(b + (size_t)c.lpc * m);  // [lpc][2]: source / destination line bases
   const int64_t L0 = (int64_t)blockIdx.x * c.lpc;
@@ -217,61 +276,28 @@ __global__ void nxc_fft_lines_kernel(const __grid_constant__ NxcFftCore c, const
   }
   for (int i = threadIdx.x; i < nl * m; i += blockDim.x) {
     const int l = i >> c.log2m, k = i & (m - 1);
-    a[i] = FUSED ? nxc_fft_fetch(g, base[2 * l], k) : c.work[(L0 + l) * m + k];
+    a[(size_t)l * m + nxc_fft_swz(k, c.swz)] = FUSED ? nxc_fft_fetch(g, base[2 * l], k) : c.work[(L0 + l) * m + k];
   }
   __syncthreads();
   int st = 0;
-  for (; st + 1 < c.log2m; st += 2) {
-    const int Ns = 1 << st;
-    for (int i = threadIdx.x; i < nl * quarter; i += blockDim.x) {
-      const int l = i >> (c.log2m - 2), j = i & (quarter - 1);
-      const double2 *x = a + (size_t)l * m;
-      double2 *y = b + (size_t)l * m;
-      const int k = j & (Ns - 1);
-      const double2 w1 = __ldg(c.tw + Ns + k);
-      const double2 w2a = __ldg(c.tw + 2 * Ns + k);
-      // exp(sign i pi (k + Ns) / 2Ns) = (sign i) w2a: a quarter turn, exact
-      const double2 w2b = c.sign < 0 ? make_double2(w2a.y, -w2a.x) : make_double2(-w2a.y, w2a.x);
-      // stage Ns: butterflies j and j + m/4
-      const double2 p0 = x[j], p1 = cmul(x[j + half], w1);
-      const double2 q0 = x[j + quarter], q1 = cmul(x[j + quarter + half], w1);
-      const double2 x0 = make_double2(p0.x + p1.x, p0.y + p1.y), x1 = make_double2(p0.x - p1.x, p0.y - p1.y);
-      const double2 y0 = make_double2(q0.x + q1.x, q0.y + q1.y), y1 = make_double2(q0.x - q1.x, q0.y - q1.y);
-      // stage 2 Ns: butterflies 2 (j - k) + k and Ns further
-      const double2 u = cmul(y0, w2a), v = cmul(y1, w2b);
-      const int o = ((j - k) << 2) + k;
-      y[o] = make_double2(x0.x + u.x, x0.y + u.y);
-      y[o + Ns] = make_double2(x1.x + v.x, x1.y + v.y);
-      y[o + 2 * Ns] = make_double2(x0.x - u.x, x0.y - u.y);
-      y[o + 3 * Ns] = make_double2(x1.x - v.x, x1.y - v.y);
+  for (int pi = 0; pi < c.npass; pi++) {
+    const int R = (c.plan >> (4 * pi)) & 15;
+    switch (R) {
+      case 2: nxc_fft_pass_r<2>(a, b, c, nl, st); break;
+      default: nxc_fft_pass_r<1>(a, b, c, nl, st); break;
     }
-    __syncthreads();
-    double2 *t = a; a = b; b = t;
-  }
-  if (st < c.log2m) {  // odd log2 m: the last stage alone, Ns = m / 2
-    const int Ns = 1 << st;
-    for (int i = threadIdx.x; i < nl * half; i += blockDim.x) {
-      const int l = i >> (c.log2m - 1), j = i & (half - 1);
-      const double2 *x = a + (size_t)l * m;
-      double2 *y = b + (size_t)l * m;
-      const int k = j & (Ns - 1);
-      const double2 u0 = x[j];
-      const double2 u1 = cmul(x[j + half], __ldg(c.tw + Ns + k));
-      const int o = ((j - k) << 1) + k;
-      y[o] = make_double2(u0.x + u1.x, u0.y + u1.y);
-      y[o + Ns] = make_double2(u0.x - u1.x, u0.y - u1.y);
-    }
-    __syncthreads();
-    double2 *t = a; a = b; b = t;
+    { double2 *t = a; a = b; b = t; }
+    st += R;
   }
   if (FUSED) {
     const int n_out = (int)sc.n_out;
     for (int i = threadIdx.x; i < nl * n_out; i += blockDim.x) {
       const int l = i / n_out, k = i - l * n_out;
-      nxc_fft_put(sc, base[2 * l + 1], k, a[(size_t)l * m + k]);
+      nxc_fft_put(sc, base[2 * l + 1], k, a[(size_t)l * m + nxc_fft_swz(k, c.swz)]);
     }
   } else {
-    for (int i = threadIdx.x; i < nl * m; i += blockDim.x) c.work[L0 * m + i] = a[i];
+    for (int i = threadIdx.x; i < nl * m; i += blockDim.x)
+      c.work[L0 * m + i] = a[(size_t)(i >> c.log2m) * m + nxc_fft_swz(i & (m - 1), c.swz)];
   }
 }
 
@@ -333,15 +359,38 @@ static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, double2 *work, const NxcFft
   ctx->launches++;
   NxcFftCore c;
   c.work = work; c.tw = tw; c.sign = sign; c.n_lines = n_lines; c.m = (int)m; c.log2m = log2m;
-  // enough lines per CTA to give 256 threads a quarter-butterfly each; long lines get more threads
-  c.lpc = (int)(m >= 1024 ? 1 : 1024 / m);
+  // pass plan: 4 stages first (its 16-element thread chunks are what the slot swizzle is built for), the rest
+  // split evenly over as few passes as 4 stages each allow
+  // stages per pass: nxc_fft_stages<R> is written for any R, and R = 3 / 4 were measured (16384 lines of 1024
+  // points: 0.26 / 0.29 ms at 76 / 128 registers against 0.22 ms for R = 2 at 48): the transform is latency-
+  // bound, so 40 resident warps per SM beat fewer shared-memory round trips
+  const int rmax = 2;
+  int rmin = rmax;
+  {
+    int rem = log2m, first = rem < rmax ? rem : rmax;
+    c.npass = 0; c.plan = 0;
+    c.plan |= first << (4 * c.npass++);
+    c.swz = first < 3 ? 3 : first;
+    rmin = first;
+    rem -= first;
+    const int cnt = (rem + rmax - 1) / rmax;
+    for (int i = 0; i < cnt; i++) {
+      const int r = (rem + cnt - 1 - i) / cnt;
+      c.plan |= r << (4 * c.npass++);
+      if (r < rmin) rmin = r;
+    }
+  }
+  // lines per CTA: enough for one group of 2^R points per thread in the pass with the most groups
+  const int64_t gmax = m >> rmin;
+  const int threads = gmax <= 256 ? 256 : (gmax >= 1024 ? 1024 : (int)gmax);
+  c.lpc = (int)(gmax >= threads ? 1 : threads / gmax);
   if (c.lpc > n_lines) c.lpc = (int)n_lines;
-  const int threads = m <= 1024 ? 256 : (m == 2048 ? 512 : 1024);
   const size_t smem = (size_t)c.lpc * (2 * (size_t)m * sizeof(double2) + 16);
+  void (*kernel)(const NxcFftCore, const NxcFftGather, const NxcFftScatter) = nxc_fft_lines_kernel<FUSED>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[FUSED]) {
-    cudaError_t e = cudaFuncSetAttribute(nxc_fft_lines_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(2 * NXC_FFT_SMEM_MAX * sizeof(double2) + 16));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * NXC_FFT_SMEM_MAX * sizeof(double2) + 16 * 256));
     if (e != cudaSuccess) { nxc_free(ctx, tw); return nxc_cuda_fail(ctx, e, "fft attribute"); }
     attr_set[FUSED] = true;
   }
@@ -350,7 +399,7 @@ static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, double2 *work, const NxcFft
   if (!FUSED) { memset(&g0, 0, sizeof g0); memset(&s0, 0, sizeof s0); g = &g0; sc = &s0; }
   const int64_t ctas = (n_lines + c.lpc - 1) / c.lpc;
   if (ctas > 0x7FFFFFFF) { nxc_free(ctx, tw); return NXC_ERR_SHAPE; }  // > 2^31 CTAs: beyond any device's memory
-  nxc_fft_lines_kernel<FUSED><<<(unsigned)ctas, threads, smem, ctx->stream>>>(c, *g, *sc);
+  kernel<<<(unsigned)ctas, threads, smem, ctx->stream>>>(c, *g, *sc);
   ctx->launches++;
   if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft lines");
   nxc_free(ctx, tw);
