@@ -11,17 +11,20 @@
 // truncation to `s`), any length n is accepted.
 //
 // How it is computed is not the reference's (a CPU mixed-radix Cooley-Tukey with per-thread
-// line scratch): each axis pass is gather -> transform -> scatter over ALL lines at once.
-//   gather   one thread per (line, k): strided read, convert to double complex, into a
-//            contiguous [lines][m] work buffer
-//   core     power-of-two self-sorting (Stockham) radix-2 transform of every line: one CTA
-//            per line with both ping-pong buffers in shared memory when m <= 4096, else
-//            log2(m) global passes over the whole buffer
-//   other n  Bluestein's chirp-z on top of the same core (m = next power of two >= 2n-1):
-//            chirp multiply in the gather, pointwise product with the transformed filter,
-//            inverse core transform, chirp multiply and 1/m in the scatter
-//   scatter  one thread per (line, k < n_out): convert to the output type, strided write
-// Twiddles are sincospi() of an exactly reduced rational angle in double precision.
+// line scratch).  Powers of two up to 4096^2 points never touch a gather / scatter pass:
+//   lines    nxc_fft_lines_kernel: a CTA reads whole lines straight from the source tensor
+//            (strided, converted to double complex, Hermitian-mirrored for irfft), runs every
+//            stage in shared memory (two radix-2 stages per pass in registers, stage-major
+//            twiddle table, swizzled slots) and writes straight to the destination tensor
+//   > 4096   four-step through the same kernel: columns of the m1 x m2 view into a work buffer,
+//            then twiddled rows with the transposed write (nxc_fft_pow2)
+//   other n  Bluestein's chirp-z (m = next power of two >= 2n-1): gather with the chirp multiply
+//            into a contiguous [lines][m] work buffer, the two forward legs and the inverse leg on
+//            the kernels above, pointwise product with the transformed filter, scatter with the
+//            chirp multiply and 1/m
+//   > 2^24   log2(m) global radix-2 passes (kept as the fallback)
+// Twiddles are sincospi() of an exactly reduced rational angle in double precision, tabulated
+// once per call.
 #include "nxc_common.cuh"
 #include "nxc_map.cuh"
 
@@ -91,6 +94,8 @@ struct NxcFftGather {
   int sign;
   int bluestein;
   int hermitian;    // irfft last axis: rebuild the length-n spectrum from n_src bins
+  const double2 *filter;  // Bluestein's second leg: element k is multiplied by filter[k] on the way in
+  const double2 *chirp;   // tabulated chirp_at(sign, k, n), k < n (NULL: computed per element)
 };
 
 __device__ __forceinline__ double2 nxc_fft_read(const void *src, int kind, int64_t off) {
@@ -116,7 +121,8 @@ __device__ __forceinline__ double2 nxc_fft_fetch(const NxcFftGather &g, int64_t 
         v.y = -v.y;
       }
     }
-    if (g.bluestein) v = cmul(v, chirp_at(g.sign, k, g.n));
+    if (g.bluestein) v = cmul(v, g.chirp ? __ldg(g.chirp + k) : chirp_at(g.sign, k, g.n));
+    if (g.filter) v = cmul(v, __ldg(g.filter + k));
   }
   return v;
 }
@@ -141,12 +147,13 @@ struct NxcFftScatter {
   int dst_kind;
   int sign;
   int bluestein;
+  const double2 *chirp;  // as NxcFftGather::chirp
 };
 
 // output element k of a line (line base `dof` in destination elements)
 __device__ __forceinline__ void nxc_fft_put(const NxcFftScatter &g, int64_t dof, int64_t k, double2 v) {
   if (g.bluestein) {
-    v = cmul(v, chirp_at(g.sign, k, g.n));
+    v = cmul(v, g.chirp ? __ldg(g.chirp + k) : chirp_at(g.sign, k, g.n));
     const double inv = 1.0 / (double)g.m;
     v.x *= inv;
     v.y *= inv;
@@ -192,14 +199,23 @@ __global__ void __launch_bounds__(256) nxc_fft_twiddle_kernel(double2 *tw, int64
   }
 }
 
+// Lines longer than NXC_FFT_SMEM_MAX take the four-step route through the same kernel: a line of
+// M = m1 m2 points is an m1 x m2 matrix; MODE_COLS transforms its m2 columns (length m1, read from
+// the source tensor, written in place into a work buffer), MODE_ROWS multiplies element (k1, n2) by
+// exp(sign 2 pi i k1 n2 / M), transforms the m1 rows (length m2) and writes row k1's bin k2 to output
+// bin k1 + m1 k2 -- two round trips through memory where log2(M) radix-2 passes took one each.
+enum { NXC_FFT_MODE_LINE = 0, NXC_FFT_MODE_COLS = 1, NXC_FFT_MODE_ROWS = 2 };
 struct NxcFftCore {
-  double2 *work;        // !FUSED: n_lines contiguous lines, transformed in place
+  double2 *work;        // four-step intermediate: [outer lines][M], written by COLS, read by ROWS
   const double2 *tw;    // m twiddles, stage-major (nxc_fft_twiddle_kernel)
+  const double2 *t_lo, *t_hi;  // ROWS: exp(sign 2 pi i e / M) = t_hi[e >> lo_bits] t_lo[e & mask]
   int sign;
-  int64_t n_lines;
+  int64_t n_lines;      // lines this launch transforms (outer lines x `other` in the four-step modes)
   int m, log2m, lpc;
   int npass, plan;      // stages taken by pass i = (plan >> 4 i) & 15
-  int swz;              // slot swizzle shift = stages of the first pass (>= 3)
+  int swz;              // slot swizzle shift (>= 3)
+  int mode, log2other, lo_bits;
+  int lfast_in, lfast_out;  // MODE_LINE along a strided axis: walk the CTA's lines fastest (adjacent lines are adjacent in memory)
 };
 
 // Shared-memory slot of element o of a line: the first pass makes thread j write the 2^R contiguous
@@ -261,22 +277,37 @@ __device__ __forceinline__ void nxc_fft_pass_r(const double2 *src, double2 *dst,
   __syncthreads();
 }
 
-template <bool FUSED>
+template <int MODE>
 __global__ void __launch_bounds__(1024) nxc_fft_lines_kernel(const __grid_constant__ NxcFftCore c, const __grid_constant__ NxcFftGather g,
-                                                            const __grid_constant__ NxcFftScatter sc) {
+                                                             const __grid_constant__ NxcFftScatter sc) {
   extern __shared__ __align__(16) unsigned char nxc_fft_smem[];
   const int m = c.m;
   double2 *a = (double2 *)nxc_fft_smem, *b = a + (size_t)c.lpc * m;
-  int64_t *base = (int64_t *)(b + (size_t)c.lpc * m);  // [lpc][2]: source / destination line bases
+  int64_t *base = (int64_t *)(b + (size_t)c.lpc * m);  // [lpc][2]: source / destination bases of the OUTER line
   const int64_t L0 = (int64_t)blockIdx.x * c.lpc;
   const int nl = (int)(c.n_lines - L0 < c.lpc ? c.n_lines - L0 : c.lpc);
-  if (FUSED) {
-    for (int l = threadIdx.x; l < nl; l += blockDim.x) nxc_fft_line_base(g.lines, L0 + l, base[2 * l], base[2 * l + 1]);
-    __syncthreads();
-  }
+  const int log2other = MODE == NXC_FFT_MODE_LINE ? 0 : c.log2other;
+  const int other = 1 << log2other;                // sub-lines per outer line
+  const int64_t M = (int64_t)m << log2other;
+  for (int l = threadIdx.x; l < nl; l += blockDim.x)
+    nxc_fft_line_base(g.lines, (L0 + l) >> log2other, base[2 * l], base[2 * l + 1]);
+  __syncthreads();
+  // load: along the line fastest, except for columns (adjacent lines are adjacent in memory)
   for (int i = threadIdx.x; i < nl * m; i += blockDim.x) {
-    const int l = i >> c.log2m, k = i & (m - 1);
-    a[(size_t)l * m + nxc_fft_swz(k, c.swz)] = FUSED ? nxc_fft_fetch(g, base[2 * l], k) : c.work[(L0 + l) * m + k];
+    int l, k;
+    if (MODE == NXC_FFT_MODE_COLS || (MODE == NXC_FFT_MODE_LINE && c.lfast_in)) { k = i / nl; l = i - k * nl; }
+    else { l = i >> c.log2m; k = i & (m - 1); }
+    const int64_t L = L0 + l;
+    const int sub = (int)(L & (other - 1));
+    double2 v;
+    if (MODE == NXC_FFT_MODE_ROWS) {
+      v = c.work[(L >> log2other) * M + (int64_t)sub * m + k];
+      const int64_t e = (int64_t)sub * k;
+      v = cmul(v, cmul(__ldg(c.t_hi + (e >> c.lo_bits)), __ldg(c.t_lo + (e & (((int64_t)1 << c.lo_bits) - 1)))));
+    } else {
+      v = nxc_fft_fetch(g, base[2 * l], MODE == NXC_FFT_MODE_COLS ? (int64_t)k * other + sub : (int64_t)k);
+    }
+    a[(size_t)l * m + nxc_fft_swz(k, c.swz)] = v;
   }
   __syncthreads();
   int st = 0;
@@ -289,15 +320,27 @@ __global__ void __launch_bounds__(1024) nxc_fft_lines_kernel(const __grid_consta
     { double2 *t = a; a = b; b = t; }
     st += R;
   }
-  if (FUSED) {
-    const int n_out = (int)sc.n_out;
+  if (MODE == NXC_FFT_MODE_LINE) {
+    const int n_out = (int)(sc.n_out < m ? sc.n_out : m);
     for (int i = threadIdx.x; i < nl * n_out; i += blockDim.x) {
-      const int l = i / n_out, k = i - l * n_out;
+      int l, k;
+      if (c.lfast_out) { k = i / nl; l = i - k * nl; }
+      else { l = i / n_out; k = i - l * n_out; }
       nxc_fft_put(sc, base[2 * l + 1], k, a[(size_t)l * m + nxc_fft_swz(k, c.swz)]);
     }
   } else {
-    for (int i = threadIdx.x; i < nl * m; i += blockDim.x)
-      c.work[L0 * m + i] = a[(size_t)(i >> c.log2m) * m + nxc_fft_swz(i & (m - 1), c.swz)];
+    for (int i = threadIdx.x; i < nl * m; i += blockDim.x) {
+      const int k = i / nl, l = i - k * nl;  // adjacent lines are adjacent outputs in both modes
+      const int64_t L = L0 + l;
+      const int sub = (int)(L & (other - 1));
+      const double2 v = a[(size_t)l * m + nxc_fft_swz(k, c.swz)];
+      if (MODE == NXC_FFT_MODE_COLS) {
+        c.work[(L >> log2other) * M + (int64_t)k * other + sub] = v;
+      } else {
+        const int64_t bin = sub + (int64_t)other * k;
+        if (bin < sc.n_out) nxc_fft_put(sc, base[2 * l + 1], bin, v);
+      }
+    }
   }
 }
 
@@ -330,6 +373,10 @@ __global__ void __launch_bounds__(256) nxc_fft_filter_kernel(double2 *bf, int64_
     bf[k] = v;
   }
 }
+__global__ void __launch_bounds__(256) nxc_fft_chirp_kernel(double2 *ch, int64_t n, int sign) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    ch[k] = chirp_at(sign, k, n);
+}
 __global__ void __launch_bounds__(256)
 nxc_fft_pointwise_kernel(double2 *work, const double2 *__restrict__ bf, int64_t n_lines, int64_t m) {
   const int64_t total = n_lines * m;
@@ -345,29 +392,29 @@ static unsigned nxc_fft_grid(nxc_ctx *ctx, int64_t items) {
   return (unsigned)b;
 }
 
-// In-place transform of n_lines contiguous lines of power-of-two length m. `tmp` is a second
-// buffer of the same size (only used when m > NXC_FFT_SMEM_MAX).
-template <bool FUSED>
-static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, double2 *work, const NxcFftGather *g, const NxcFftScatter *sc,
-                                       int64_t n_lines, int64_t m, int sign) {
-  int log2m = 0;
-  while (((int64_t)1 << log2m) < m) log2m++;
+static int nxc_fft_log2(int64_t m) {
+  int l = 0;
+  while (((int64_t)1 << l) < m) l++;
+  return l;
+}
+
+// One launch of the lines kernel: `n_lines` lines of m <= NXC_FFT_SMEM_MAX points in `mode`.
+static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, NxcFftCore c, const NxcFftGather &g, const NxcFftScatter &sc) {
+  const int64_t m = c.m;
+  c.log2m = nxc_fft_log2(m);
   double2 *tw = NULL;
   nxc_status s = nxc_alloc(ctx, sizeof(double2) * (size_t)m, (void **)&tw);
   if (s) return s;
-  nxc_fft_twiddle_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(tw, m, sign);
+  nxc_fft_twiddle_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(tw, m, c.sign);
   ctx->launches++;
-  NxcFftCore c;
-  c.work = work; c.tw = tw; c.sign = sign; c.n_lines = n_lines; c.m = (int)m; c.log2m = log2m;
-  // pass plan: 4 stages first (its 16-element thread chunks are what the slot swizzle is built for), the rest
-  // split evenly over as few passes as 4 stages each allow
+  c.tw = tw;
   // stages per pass: nxc_fft_stages<R> is written for any R, and R = 3 / 4 were measured (16384 lines of 1024
   // points: 0.26 / 0.29 ms at 76 / 128 registers against 0.22 ms for R = 2 at 48): the transform is latency-
   // bound, so 40 resident warps per SM beat fewer shared-memory round trips
   const int rmax = 2;
   int rmin = rmax;
   {
-    int rem = log2m, first = rem < rmax ? rem : rmax;
+    int rem = c.log2m, first = rem < rmax ? rem : rmax;
     c.npass = 0; c.plan = 0;
     c.plan |= first << (4 * c.npass++);
     c.swz = first < 3 ? 3 : first;
@@ -380,37 +427,111 @@ static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, double2 *work, const NxcFft
       if (r < rmin) rmin = r;
     }
   }
-  // lines per CTA: enough for one group of 2^R points per thread in the pass with the most groups
+  // lines per CTA: enough for one group of 2^R points per thread in the pass with the most groups; the
+  // four-step modes want at least two (their strided side then moves whole 32-byte sectors)
   const int64_t gmax = m >> rmin;
-  const int threads = gmax <= 256 ? 256 : (gmax >= 1024 ? 1024 : (int)gmax);
-  c.lpc = (int)(gmax >= threads ? 1 : threads / gmax);
-  if (c.lpc > n_lines) c.lpc = (int)n_lines;
+  c.lpc = (int)(gmax >= 256 ? 1 : 256 / gmax);
+  if (c.mode != NXC_FFT_MODE_LINE && c.lpc < 2 && m <= NXC_FFT_SMEM_MAX / 2) c.lpc = 2;
+  if (c.mode == NXC_FFT_MODE_LINE) {
+    c.lfast_in = g.stride != 1 && g.stride != -1;
+    c.lfast_out = sc.stride != 1 && sc.stride != -1;
+    // a strided axis: as many adjacent lines per CTA as the two buffers hold, up to a 128-byte run
+    if (c.lfast_in || c.lfast_out)
+      while (c.lpc < 8 && (int64_t)c.lpc * 2 * m <= NXC_FFT_SMEM_MAX) c.lpc *= 2;
+  }
+  if (c.lpc > c.n_lines) c.lpc = (int)c.n_lines;
+  int64_t want = gmax * c.lpc;
+  const int threads = want <= 256 ? 256 : (want >= 1024 ? 1024 : (int)want);
   const size_t smem = (size_t)c.lpc * (2 * (size_t)m * sizeof(double2) + 16);
-  void (*kernel)(const NxcFftCore, const NxcFftGather, const NxcFftScatter) = nxc_fft_lines_kernel<FUSED>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[FUSED]) {
+  void (*kernel)(const NxcFftCore, const NxcFftGather, const NxcFftScatter) =
+      c.mode == NXC_FFT_MODE_LINE ? nxc_fft_lines_kernel<NXC_FFT_MODE_LINE>
+                                  : (c.mode == NXC_FFT_MODE_COLS ? nxc_fft_lines_kernel<NXC_FFT_MODE_COLS>
+                                                                 : nxc_fft_lines_kernel<NXC_FFT_MODE_ROWS>);
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[c.mode]) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * NXC_FFT_SMEM_MAX * sizeof(double2) + 16 * 256));
     if (e != cudaSuccess) { nxc_free(ctx, tw); return nxc_cuda_fail(ctx, e, "fft attribute"); }
-    attr_set[FUSED] = true;
+    attr_set[c.mode] = true;
   }
-  NxcFftGather g0;
-  NxcFftScatter s0;
-  if (!FUSED) { memset(&g0, 0, sizeof g0); memset(&s0, 0, sizeof s0); g = &g0; sc = &s0; }
-  const int64_t ctas = (n_lines + c.lpc - 1) / c.lpc;
+  const int64_t ctas = (c.n_lines + c.lpc - 1) / c.lpc;
   if (ctas > 0x7FFFFFFF) { nxc_free(ctx, tw); return NXC_ERR_SHAPE; }  // > 2^31 CTAs: beyond any device's memory
-  kernel<<<(unsigned)ctas, threads, smem, ctx->stream>>>(c, *g, *sc);
+  kernel<<<(unsigned)ctas, threads, smem, ctx->stream>>>(c, g, sc);
   ctx->launches++;
   if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft lines");
   nxc_free(ctx, tw);
   return s;
 }
 
+__global__ void __launch_bounds__(256) nxc_fft_split_twiddle_kernel(double2 *t_lo, double2 *t_hi, int lo_bits, int hi_bits,
+                                                                    int64_t M, int sign) {
+  const int64_t nlo = (int64_t)1 << lo_bits, nhi = (int64_t)1 << hi_bits;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nlo + nhi; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nlo) t_lo[i] = cispi(sign, 2 * i, M);
+    else t_hi[i - nlo] = cispi(sign, 2 * ((i - nlo) << lo_bits), M);
+  }
+}
+
+// Power-of-two transform of `n_outer` lines of m points described by a gather / scatter pair (any
+// source / destination the descriptors can address): one launch up to NXC_FFT_SMEM_MAX points, the
+// four-step pair of launches through `work` ([n_outer][m] double2) up to NXC_FFT_SMEM_MAX^2.
+static nxc_status nxc_fft_pow2(nxc_ctx *ctx, const NxcFftGather &g, const NxcFftScatter &sc, int64_t n_outer, int64_t m,
+                               int sign, double2 *work) {
+  NxcFftCore c;
+  memset(&c, 0, sizeof c);
+  c.sign = sign;
+  if (m <= NXC_FFT_SMEM_MAX) {
+    c.mode = NXC_FFT_MODE_LINE; c.m = (int)m; c.n_lines = n_outer; c.log2other = 0;
+    return nxc_fft_lines_launch(ctx, c, g, sc);
+  }
+  const int log2M = nxc_fft_log2(m), l1 = log2M / 2, l2 = log2M - l1;  // columns of 2^l1 points, rows of 2^l2
+  double2 *tt = NULL;
+  const int lo_bits = (log2M + 1) / 2, hi_bits = log2M - lo_bits;
+  nxc_status s = nxc_alloc(ctx, sizeof(double2) * (((size_t)1 << lo_bits) + ((size_t)1 << hi_bits)), (void **)&tt);
+  if (s) return s;
+  nxc_fft_split_twiddle_kernel<<<64, 256, 0, ctx->stream>>>(tt, tt + ((size_t)1 << lo_bits), lo_bits, hi_bits, m, sign);
+  ctx->launches++;
+  c.work = work;
+  c.mode = NXC_FFT_MODE_COLS; c.m = 1 << l1; c.log2other = l2; c.n_lines = n_outer << l2;
+  s = nxc_fft_lines_launch(ctx, c, g, sc);
+  if (!s) {
+    c.mode = NXC_FFT_MODE_ROWS; c.m = 1 << l2; c.log2other = l1; c.n_lines = n_outer << l1;
+    c.t_lo = tt; c.t_hi = tt + ((size_t)1 << lo_bits); c.lo_bits = lo_bits;
+    s = nxc_fft_lines_launch(ctx, c, g, sc);
+  }
+  nxc_free(ctx, tt);
+  return s;
+}
+
+// gather / scatter descriptors of n_lines contiguous double-complex lines of m points at `buf`
+static void nxc_fft_contig(double2 *buf, int64_t n_lines, int64_t m, NxcFftGather *g, NxcFftScatter *sc) {
+  memset(g, 0, sizeof *g);
+  memset(sc, 0, sizeof *sc);
+  NxcFftLines ln;
+  memset(&ln, 0, sizeof ln);
+  ln.n = 1;
+  ln.shape[0] = n_lines; ln.src_stride[0] = m; ln.dst_stride[0] = m;
+  ln.small = n_lines < 0x7FFFFFFFLL;
+  ln.div[0] = nxc_fastdiv_make(ln.small ? (uint32_t)n_lines : 1u);
+  g->lines = ln; g->src = buf; g->n_lines = n_lines; g->n = m; g->n_src = m; g->m = m; g->stride = 1;
+  g->src_kind = NXC_FFT_SRC_C64;
+  sc->lines = ln; sc->dst = buf; sc->n_lines = n_lines; sc->n = m; sc->n_out = m; sc->m = m; sc->stride = 1;
+  sc->dst_kind = NXC_FFT_SRC_C64;
+}
+
+// In-place transform of n_lines contiguous lines of power-of-two length m (the Bluestein legs).
+// `tmp` is a second buffer of the same size, used when m > NXC_FFT_SMEM_MAX.
 static nxc_status nxc_fft_core(nxc_ctx *ctx, double2 *work, double2 *tmp, int64_t n_lines, int64_t m, int sign) {
-  int log2m = 0;
-  while (((int64_t)1 << log2m) < m) log2m++;
+  const int log2m = nxc_fft_log2(m);
   if (log2m == 0) return NXC_OK;
-  if (m <= NXC_FFT_SMEM_MAX) return nxc_fft_lines_launch<false>(ctx, work, NULL, NULL, n_lines, m, sign);
+  if (m <= (int64_t)NXC_FFT_SMEM_MAX * NXC_FFT_SMEM_MAX) {
+    NxcFftGather g;
+    NxcFftScatter sc;
+    nxc_fft_contig(work, n_lines, m, &g, &sc);
+    // long lines: columns go work -> tmp, rows tmp -> work (each CTA's reads and writes are the same elements
+    // only in the single-launch case, where a line is wholly in shared memory before it is written)
+    return nxc_fft_pow2(ctx, g, sc, n_lines, m, sign, tmp);
+  }
   double2 *a = work, *b = tmp;
   for (int st = 0; st < log2m; st++) {
     nxc_fft_global_pass_kernel<<<nxc_fft_grid(ctx, n_lines * (m / 2)), 256, 0, ctx->stream>>>(a, b, n_lines, m, st, sign);
@@ -457,23 +578,81 @@ static nxc_status nxc_fft_pass(nxc_ctx *ctx, const NxcFftPass &p) {
     m = 1;
     while (m < 2 * p.n - 1) m <<= 1;
   }
-  if (pow2 && m >= 2 && m <= NXC_FFT_SMEM_MAX) {
-    // one kernel: source tensor -> shared memory -> destination tensor
+  if (pow2 && m >= 2 && m <= (int64_t)NXC_FFT_SMEM_MAX * NXC_FFT_SMEM_MAX) {
+    // source tensor -> shared memory -> destination tensor, once (twice through a work buffer for long lines)
     NxcFftGather g;
     g.lines = ln;
     g.src = (const char *)src->data + src->offset * nxc_fft_esize(p.src_kind);
     g.work = NULL;
     g.n_lines = n_lines; g.n = p.n; g.n_src = p.n_src; g.m = m;
     g.stride = src->strides[p.axis];
-    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = 0; g.hermitian = p.hermitian;
+    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = 0; g.hermitian = p.hermitian; g.filter = NULL; g.chirp = NULL;
     NxcFftScatter sc;
     sc.lines = ln;
     sc.dst = (char *)dst->data + dst->offset * nxc_fft_esize(p.dst_kind);
     sc.work = NULL;
     sc.n_lines = n_lines; sc.n = p.n; sc.n_out = p.n_out; sc.m = m;
     sc.stride = dst->strides[p.axis];
-    sc.dst_kind = p.dst_kind; sc.sign = p.sign; sc.bluestein = 0;
-    return nxc_fft_lines_launch<true>(ctx, NULL, &g, &sc, n_lines, m, p.sign);
+    sc.dst_kind = p.dst_kind; sc.sign = p.sign; sc.bluestein = 0; sc.chirp = NULL;
+    double2 *mid = NULL;
+    nxc_status s4 = NXC_OK;
+    if (m > NXC_FFT_SMEM_MAX) s4 = nxc_alloc(ctx, sizeof(double2) * (size_t)n_lines * (size_t)m, (void **)&mid);
+    if (!s4) s4 = nxc_fft_pow2(ctx, g, sc, n_lines, m, p.sign, mid);
+    if (mid) nxc_free(ctx, mid);
+    return s4;
+  }
+  if (!pow2 && m <= (int64_t)NXC_FFT_SMEM_MAX * NXC_FFT_SMEM_MAX) {
+    // Bluestein in two transforms: (source x chirp, zero-padded) -> work, then (work x filter) -> inverse
+    // transform -> (x chirp / m) -> destination; the chirp, the filter product and the final scaling ride on
+    // the lines kernel's loads and stores
+    double2 *work = NULL, *mid = NULL, *bf = NULL;
+    nxc_status sb = nxc_alloc(ctx, sizeof(double2) * (size_t)n_lines * (size_t)m, (void **)&work);
+    if (!sb && m > NXC_FFT_SMEM_MAX) sb = nxc_alloc(ctx, sizeof(double2) * (size_t)n_lines * (size_t)m, (void **)&mid);
+    if (!sb) sb = nxc_alloc(ctx, sizeof(double2) * ((size_t)m * 2 + (size_t)p.n), (void **)&bf);
+    double2 *chirp = bf ? bf + 2 * m : NULL;
+    if (!sb) {
+      nxc_fft_filter_kernel<<<nxc_fft_grid(ctx, m), 256, 0, ctx->stream>>>(bf, p.n, m, p.sign);
+      nxc_fft_chirp_kernel<<<nxc_fft_grid(ctx, p.n), 256, 0, ctx->stream>>>(chirp, p.n, p.sign);
+      ctx->launches += 2;
+      sb = nxc_fft_core(ctx, bf, bf + m, 1, m, -1);
+    }
+    NxcFftGather gw;
+    NxcFftScatter sw;
+    nxc_fft_contig(work, n_lines, m, &gw, &sw);
+    // the lines kernel takes BOTH line bases from the gather's descriptor: the tensor's line numbering with
+    // the work buffer's contiguous strides on the other side
+    NxcFftLines to_work = ln, from_work = ln;
+    {
+      int64_t st = m;
+      for (int i = ln.n - 1; i >= 0; i--) { to_work.dst_stride[i] = st; from_work.src_stride[i] = st; st *= ln.shape[i]; }
+    }
+    if (!sb) {
+      NxcFftGather g;
+      memset(&g, 0, sizeof g);
+      g.lines = to_work;
+      g.src = (const char *)src->data + src->offset * nxc_fft_esize(p.src_kind);
+      g.n_lines = n_lines; g.n = p.n; g.n_src = p.n_src; g.m = m;
+      g.stride = src->strides[p.axis];
+      g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = 1; g.hermitian = p.hermitian; g.chirp = chirp;
+      // the work lines take the source tensor's line numbering: same count, contiguous
+      sb = nxc_fft_pow2(ctx, g, sw, n_lines, m, -1, mid);
+    }
+    if (!sb) {
+      NxcFftScatter sc;
+      memset(&sc, 0, sizeof sc);
+      sc.lines = ln;
+      sc.dst = (char *)dst->data + dst->offset * nxc_fft_esize(p.dst_kind);
+      sc.n_lines = n_lines; sc.n = p.n; sc.n_out = p.n_out; sc.m = m;
+      sc.stride = dst->strides[p.axis];
+      sc.dst_kind = p.dst_kind; sc.sign = p.sign; sc.bluestein = 1; sc.chirp = chirp;
+      gw.filter = bf;
+      gw.lines = from_work;
+      sb = nxc_fft_pow2(ctx, gw, sc, n_lines, m, +1, mid);
+    }
+    if (work) nxc_free(ctx, work);
+    if (mid) nxc_free(ctx, mid);
+    if (bf) nxc_free(ctx, bf);
+    return sb;
   }
   const size_t wbytes = sizeof(double2) * (size_t)n_lines * (size_t)m;
   double2 *work = NULL, *tmp = NULL, *bf = NULL;
@@ -488,7 +667,7 @@ static nxc_status nxc_fft_pass(nxc_ctx *ctx, const NxcFftPass &p) {
     g.work = work;
     g.n_lines = n_lines; g.n = p.n; g.n_src = p.n_src; g.m = m;
     g.stride = src->strides[p.axis];
-    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = !pow2; g.hermitian = p.hermitian;
+    g.src_kind = p.src_kind; g.sign = p.sign; g.bluestein = !pow2; g.hermitian = p.hermitian; g.filter = NULL; g.chirp = NULL;
     nxc_fft_gather_kernel<<<nxc_fft_grid(ctx, n_lines * m), 256, 0, ctx->stream>>>(g);
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft gather");
@@ -515,7 +694,7 @@ static nxc_status nxc_fft_pass(nxc_ctx *ctx, const NxcFftPass &p) {
     g.work = work;
     g.n_lines = n_lines; g.n = p.n; g.n_out = p.n_out; g.m = m;
     g.stride = dst->strides[p.axis];
-    g.dst_kind = p.dst_kind; g.sign = p.sign; g.bluestein = !pow2;
+    g.dst_kind = p.dst_kind; g.sign = p.sign; g.bluestein = !pow2; g.chirp = NULL;
     nxc_fft_scatter_kernel<<<nxc_fft_grid(ctx, n_lines * p.n_out), 256, 0, ctx->stream>>>(g);
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) s = nxc_cuda_fail(ctx, cudaGetLastError(), "fft scatter");

@@ -78,6 +78,40 @@ def test_fft_long_lines_match_reference(ctx, oracle):
         _close(back / n, x.numpy(), "c64", f"ifft(fft)/long/{shape}")
 
 
+def test_fft_four_step_lines(ctx, oracle):
+    """Lines beyond 4096 points go through the lines kernel twice (columns, then twiddled rows with
+    a transposed write -- nxc_fft.cu, nxc_fft_pow2): even and odd log2 splits, batched, along a
+    strided axis, c32 storage, a long Bluestein length (its power-of-two legs take the same
+    route), rfft / irfft with the Hermitian rebuild and a truncated output, and in-place
+    multi-axis -- against the reference binary, and numpy's pocketfft for the longest line."""
+    if oracle.__name__.endswith("nxo"):
+        pytest.skip("reference binary not available")
+    rng = np.random.default_rng(16)
+    for dt, shape, axes in (("c64", (3, 8192), [1]), ("c64", (2, 32768), [1]), ("c64", (8192, 5), [0]),
+                            ("c32", (2, 16384), [1]), ("c64", (2, 9001), [1]), ("c64", (8192, 8), [0, 1])):
+        x = _mk(rng, shape, dt)
+        want = oracle.fft(x, axes, False).numpy()
+        got = H.download(B.fft(H.upload(ctx, x), axes))
+        _close(got, want, dt, f"fft/four-step/{dt}/{shape}/{axes}")
+        want = oracle.fft(x, axes, True).numpy()
+        got = H.download(B.ifft(H.upload(ctx, x), axes))
+        _close(got, want, dt, f"ifft/four-step/{dt}/{shape}/{axes}")
+    for rdt, cdt, shape in (("f64", "c64", (2, 16384)), ("f32", "c32", (3, 8192))):
+        x = _mk(rng, shape, rdt)
+        want = oracle.rfft(x, cdt, [1])
+        got = H.download(B.rfft(H.upload(ctx, x), cdt, [1]))
+        _close(got, want.numpy(), cdt, f"rfft/four-step/{shape}")
+        for s in (None, [shape[1] - 100], [shape[1]]):
+            w = oracle.irfft(want, rdt, [1], s).numpy()
+            g = H.download(B.irfft(H.upload(ctx, want), rdt, [1], s))
+            _close(g, w, rdt, f"irfft/four-step/{shape}/s={s}")
+    n = 1 << 21
+    z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    got = H.download(B.fft(H.upload(ctx, H.HostView.from_array(z, "c64")), [0]))
+    want = np.fft.fft(z)
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("rdt,cdt", [("f32", "c32"), ("f64", "c64")])
 def test_rfft_irfft(ctx, oracle, rdt, cdt):
     rng = np.random.default_rng(14)
