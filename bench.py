@@ -197,6 +197,32 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # DRAM traffic of the dominant kernel, measured in this run (one ncu pass over a probe process)
 # ---------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device_index):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so that the pinned staging
+    buffers allocated afterwards are first-touched on that node (local-allocation policy) and the
+    e2e copies do not cross the socket interconnect: at N = 8 the host's memory system is the
+    limiter. Returns what was done, for the JSON line; None when the
+    topology is not visible (no sysfs entry, a single node, a VM reporting -1)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0 or not os.path.isdir("/sys/devices/system/node/node1"):
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def measure_traffic(log2n):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if os.environ.get("NX_BENCH_NO_NCU") == "1" or not os.path.exists(ncu):
@@ -552,6 +578,8 @@ def main():
     # pinned host buffers: inputs go up through the upload engine, all three elementwise results come
     # back through the download engine (nxc_d2h_async), so step i's read-backs overlap step i+1's
     # upload -- both PCIe directions busy; the small reduction results use the blocking to_host
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch.cuda.current_device())
     pa, pb = (ctx.pinned_empty(n, np.float32) for _ in range(2))
     pr = [ctx.pinned_empty(n, np.float32) for _ in range(3)]
     pa[:] = np.tile(ha, n // blk)
@@ -594,7 +622,9 @@ def main():
            "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3),
            "steps": e2e_steps, "host_wall_ms_of_each_step": per_step,
            # what limits it: each rank moves this much over its own PCIe link per step, both directions at once
-           "pcie_gbs_per_rank": {"h2d": round(2 * nbytes / e2e_local / 1e9, 1), "d2h": round(d2h / e2e_local / 1e9, 1)}}
+           "pcie_gbs_per_rank": {"h2d": round(2 * nbytes / e2e_local / 1e9, 1), "d2h": round(d2h / e2e_local / 1e9, 1)},
+           # staging buffers placed on the GPU's own NUMA node (null: topology not visible, nothing bound)
+           "numa_binding_rank0": numa}
     # the last step's read-backs are complete (sync_all above drains the device): check all three
     # against the host inputs -- add and mul bit for bit over the whole array, sin within 2 ulp on a sample
     if not np.array_equal(pr[0], pa + pb):
@@ -610,6 +640,7 @@ def main():
     checks["e2e_readbacks_match_host"] = True
     del pa, pb, pr, a, b, A
     ctx.sync()
+    os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every core again
 
     # ---- BASELINE.json configs[3] and configs[4] through the same backend ----------------------
     mlp_grad = gpt2 = None
