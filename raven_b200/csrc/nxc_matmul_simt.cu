@@ -317,7 +317,10 @@ nxc_status nxc_matmul_simt(nxc_ctx *ctx, const NxcMatmulProblem &p) {
     bt.as_[i] = p.as_[i]; bt.bs_[i] = p.bs_[i]; bt.cs_[i] = p.cs_[i];
   }
   if (p.nbatch >= 0x7FFFFFFFLL) return NXC_ERR_SHAPE;
-  if ((p.dt == NXC_F32 || p.dt == NXC_F64) && p.m >= 64 && p.n >= 64 && p.k >= 8)
+  // the 128 x 128 kernel once its grid covers the SMs; below that the 64 x 64 tiles of the generic kernel put four
+  // times as many CTAs on the device (f32 256^3: 4 CTAs took 61 us)
+  const int64_t big_ctas = ((p.m + MB_M - 1) / MB_M) * ((p.n + MB_N - 1) / MB_N) * p.nbatch;
+  if ((p.dt == NXC_F32 || p.dt == NXC_F64) && p.m >= 64 && p.n >= 64 && p.k >= 8 && big_ctas >= ctx->sm_count)
     return p.dt == NXC_F32 ? launch_big<float>(ctx, p, bt) : launch_big<double>(ctx, p, bt);
   dim3 grid((unsigned)((p.n + MM_BN - 1) / MM_BN), (unsigned)((p.m + MM_BM - 1) / MM_BM),
             (unsigned)(p.nbatch < 65535 ? p.nbatch : 65535));
