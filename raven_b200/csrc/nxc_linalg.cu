@@ -1135,22 +1135,24 @@ __global__ void __launch_bounds__(NXC_LA_THREADS) nxc_svd_kernel(const NxcSvdArg
 struct NxcEigArgs {
   Cd *h, *z, *x, *vo, *w, *vs, *rs;
   double *rc, *bal;
+  int *flag;
   int64_t n;
   int vectors;
   int smem_rows;
   int *status;
 };
 
-__global__ void __launch_bounds__(NXC_LA_THREADS) nxc_eig_kernel(const __grid_constant__ NxcEigArgs a) {
+__global__ void __launch_bounds__(NXC_LA_THREADS, 2) nxc_eig_kernel(const __grid_constant__ NxcEigArgs a) {
   __shared__ double red[NXC_LA_THREADS];
   extern __shared__ __align__(16) unsigned char eig_smem[];
   const int64_t b = blockIdx.x, n = a.n, nn = a.n * a.n;
   // the Householder vector and the rotation chain are read by every thread at every step: keep them in
-  // shared memory when they fit (40 bytes per row), in global scratch otherwise
+  // shared memory when they fit (44 bytes per row, with the wavefront's flags), in global scratch otherwise
   Cd *vs = a.smem_rows ? (Cd *)eig_smem : a.vs + b * n;
   Cd *rs = a.smem_rows ? vs + n : a.rs + b * n;
   double *rc = a.smem_rows ? (double *)(rs + n) : a.rc + b * n;
-  la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, vs, rc, rs,
+  int *flag = a.smem_rows ? (int *)(rc + n) : a.flag + b * n;
+  la3_eig_body(nxc_la3_thr(), a.h + b * nn, a.z + b * nn, a.x + b * nn, a.vo + b * nn, a.w + b * n, vs, rc, rs, flag,
                a.bal + b * n, red, n, a.vectors, a.status);
 }
 
@@ -1286,7 +1288,7 @@ extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tenso
   const size_t o_h = carve(nb * nn * 16), o_z = carve(nb * nn * 16);
   const size_t o_x = carve(vectors ? nb * nn * 16 : 16), o_vo = carve(vectors ? nb * nn * 16 : 16);
   const size_t o_w = carve(nb * n * 16), o_vs = carve(nb * n * 16), o_rs = carve(nb * n * 16), o_rc = carve(nb * n * 8);
-  const size_t o_bal = carve(nb * n * 8);
+  const size_t o_bal = carve(nb * n * 8), o_flag = carve(nb * n * 4);
   const size_t o_st = carve(sizeof(int));
   char *base = NULL;
   if ((s = nxc_alloc(ctx, off, (void **)&base))) return nxc_la_fail(ctx, s);
@@ -1298,8 +1300,9 @@ extern "C" nxc_status nxc_eig(nxc_ctx *ctx, const nxc_tensor *w, const nxc_tenso
     NxcEigArgs a;
     a.h = (Cd *)(base + o_h); a.z = (Cd *)(base + o_z); a.x = (Cd *)(base + o_x); a.vo = (Cd *)(base + o_vo);
     a.w = (Cd *)(base + o_w); a.vs = (Cd *)(base + o_vs); a.rs = (Cd *)(base + o_rs); a.rc = (double *)(base + o_rc); a.bal = (double *)(base + o_bal);
+    a.flag = (int *)(base + o_flag);
     a.n = n; a.vectors = vectors; a.status = (int *)(base + o_st);
-    size_t smem = (size_t)n * 40;
+    size_t smem = (size_t)n * 44;
     a.smem_rows = smem <= 160 * 1024;
     if (!a.smem_rows) smem = 0;
     if (smem > 40 * 1024) cudaFuncSetAttribute(nxc_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

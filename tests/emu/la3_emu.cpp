@@ -52,12 +52,13 @@ extern "C" int la3_emu_eig(const double *a, int64_t n, int vectors, double *w, d
   Cd *rs = (Cd *)calloc((size_t)n + 1, sizeof(Cd));
   double *rc = (double *)calloc((size_t)n + 1, sizeof(double));
   double *bal = (double *)calloc((size_t)n + 1, sizeof(double));
+  int *flag = (int *)calloc((size_t)n + 1, sizeof(int));
   double red[1];
   int status = 0;
   memcpy(h, a, (size_t)(n * n) * sizeof(Cd));
   La3Thr t = {0, 1, 0, 1, 0, 1};
-  la3_eig_body(t, h, z, x, (Cd *)v, (Cd *)w, vs, rc, rs, bal, red, n, vectors, &status);
-  free(h); free(z); free(x); free(vs); free(rs); free(rc); free(bal);
+  la3_eig_body(t, h, z, x, (Cd *)v, (Cd *)w, vs, rc, rs, flag, bal, red, n, vectors, &status);
+  free(h); free(z); free(x); free(vs); free(rs); free(rc); free(bal); free(flag);
   return status;
 }
 
