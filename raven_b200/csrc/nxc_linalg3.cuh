@@ -22,10 +22,11 @@
 //   eig: everything in complex double (the output type): Householder reduction to Hessenberg form
 //        with the transforms accumulated, then the explicitly shifted QR iteration (Wilkinson
 //        shift, exceptional shifts at 10 / 20, a 30 n iteration cap -> no-convergence status, the
-//        same discipline as nx_c_eig.c:44-52): the left Givens pass costs one barrier per column
-//        (the thread that owns column k has just finished it and publishes G_k), the right pass
-//        and the accumulation into Z are barrier-free (a thread owns a row and applies the whole
-//        rotation chain). Eigenvectors: one thread per eigenvalue back-substitutes on the
+//        same discipline as nx_c_eig.c:44-52): the left Givens pass is a wavefront without
+//        barriers (a thread carries its column down the chain and meets G_k as soon as the thread
+//        that owns column k has published it through a flag), the right pass and the accumulation
+//        into Z (kept transposed, so these row walks coalesce) are barrier-free too (a thread owns
+//        a row and applies the whole rotation chain). Eigenvectors: one thread per eigenvalue back-substitutes on the
 //        triangular Schur factor, then V = Z X and a column normalisation.
 // The bodies are __host__ __device__ over an explicit thread descriptor so that tests/emu can run
 // the very same code single-threaded on the CPU (tests only; the product has no CPU path).
@@ -80,6 +81,13 @@ NXC_HD void la3_await(const int *flag, int stamp, int far) {
 NXC_HD void la3_syncwarp() {
 #ifdef __CUDA_ARCH__
   __syncwarp();
+#endif
+}
+NXC_HD double la3_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
 #endif
 }
 NXC_HD double la3_warp_sum(double v) {
@@ -697,6 +705,8 @@ NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd
     for (int64_t j = l + t.tid; j < n; j += t.nt) {
       const int64_t kend = j < hi ? j : hi;
       Cd u0 = h[l * n + j];
+      // the subdiagonal entry G_j is made from: asked for now, its L2 round trip is over when the chain arrives
+      const Cd b0 = j < hi ? h[(j + 1) * n + j] : cmk(0.0, 0.0);
       for (int64_t k = l; k < kend; k++) {
         const Cd u1 = h[(k + 1) * n + j];
         la3_await(&flag[k], stamp, j - k > 48);
@@ -708,7 +718,6 @@ NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd
       if (j < hi) {
         // (these few flops sit on the critical path of every column: one scaling division and two
         // square roots instead of three hypot calls)
-        const Cd b0 = h[(j + 1) * n + j];
         Cd a = u0, b = b0;
         double c = 1.0;
         Cd s = cmk(0.0, 0.0);
@@ -723,7 +732,7 @@ NXC_HD void la3_eig_body(const La3Thr &t, Cd *h, Cd *z, Cd *x, Cd *vo, Cd *w, Cd
           const double na2 = cnorm2(a), nb2 = cnorm2(b);
           if (na2 == 0.0) { c = 0.0; s = cscale(cconj(b), 1.0 / sqrt(nb2)); }
           else {
-            const double ina = 1.0 / sqrt(na2), ir = 1.0 / sqrt(na2 + nb2);
+            const double ina = la3_rsqrt(na2), ir = la3_rsqrt(na2 + nb2);
             c = na2 * ina * ir;
             s = cscale(cmul(a, cconj(b)), ir * ina);
           }
