@@ -118,6 +118,39 @@ nxc_status nxc_matmul_f32x3(nxc_ctx *ctx, const NxcMatmulProblem &q) {
     p.bs_[i] = (b_b && q.bshape[i] > 1) ? ext * q.n * 3 * kp : 0;
     ext *= q.bshape[i];
   }
+  // A short, wide-K product leaves most SM pairs idle and is one long dependent K loop (a 256 x 768 x 768 linear
+  // of the GPT-2 step at its reference batch: 12 tile pairs, 36 k-blocks each). Its three sections are three
+  // independent products lo*hi, hi*lo, hi*hi: run them as three BATCHES of K = kp into a workspace and add the
+  // partials in that fixed order (the two cross terms first), one small fold kernel. Same arithmetic per section,
+  // a third of the chain, three times the CTAs.
+  const int64_t max_ctas = ((q.m + 127) / 128) * ((q.n + 63) / 64);
+  if (q.nbatch == 1 && kp >= 256 && max_ctas * 3 <= ctx->sm_count && !getenv("NX_CUDA_X3_NO_SPLIT")) {
+    float *ws = NULL;
+    if ((s = nxc_alloc(ctx, (size_t)(3 * q.m * q.n) * sizeof(float), (void **)&ws))) { nxc_free(ctx, a3); nxc_free(ctx, b3); return s; }
+    NxcMatmulProblem ps = p;
+    ps.k = kp;
+    ps.batch_nd = 1; ps.nbatch = 3; ps.bshape[0] = 3;
+    ps.as_[0] = kp; ps.bs_[0] = kp; ps.cs_[0] = q.m * q.n;
+    ps.c = (char *)ws; ps.c_rs = q.n; ps.c_cs = 1;
+    s = nxc_matmul_tc(ctx, ps);
+    if (!s) {
+      nxc_tensor wd, cd;
+      memset(&wd, 0, sizeof wd);
+      memset(&cd, 0, sizeof cd);
+      wd.data = ws; wd.dtype = NXC_F32; wd.ndim = 3;
+      wd.shape[0] = 3; wd.shape[1] = q.m; wd.shape[2] = q.n;
+      wd.strides[0] = q.m * q.n; wd.strides[1] = q.n; wd.strides[2] = 1;
+      cd.data = (void *)q.c; cd.dtype = NXC_F32; cd.ndim = 2;
+      cd.shape[0] = q.m; cd.shape[1] = q.n;
+      cd.strides[0] = q.c_rs; cd.strides[1] = q.c_cs;
+      const int axis0 = 0;
+      s = nxc_reduce(ctx, NXC_SUM, &cd, &wd, &axis0, 1);
+    }
+    nxc_free(ctx, ws);
+    nxc_free(ctx, a3);
+    nxc_free(ctx, b3);
+    return s;
+  }
   s = nxc_matmul_tc(ctx, p);
   nxc_free(ctx, a3);   // stream-ordered: reused only after the GEMM that reads them
   nxc_free(ctx, b3);

@@ -340,3 +340,38 @@ def test_matmul_broadcast_weight_batches_fold_into_rows(ctx, oracle, dtype):
         else:
             bound = float((np.abs(X.reshape(-1, C)).astype(np.float64) @ np.abs(W).astype(np.float64)).max())
             assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 2e-5 * bound, name
+
+
+def test_matmul_f32_short_wide_k_runs_its_three_sections_as_batches(ctx, oracle, monkeypatch):
+    """A 3xTF32 product with few output tiles and K >= 256 (a 256 x 768 x 768 linear of the GPT-2
+    step at the reference's batch) runs its lo*hi, hi*lo and hi*hi sections as three batches and
+    adds the partials with one fold (nxc_matmul_x3.cu): same accuracy class against the reference
+    binary, the same result as the single-chain form to rounding, strided output rows, a K that is
+    not a multiple of 32, and an infinite operand."""
+    rng = np.random.default_rng(12)
+    for m, k, n in ((256, 768, 768), (64, 4104, 512), (300, 2048, 256)):
+        A = rng.standard_normal((m, k)).astype(np.float32)
+        Bm = rng.standard_normal((k, n)).astype(np.float32)
+        a = H.HostView(A.reshape(-1).copy(), "f32", [m, k])
+        b = H.HostView(Bm.reshape(-1).copy(), "f32", [k, n])
+        bt = H.HostView(np.ascontiguousarray(Bm.T).reshape(-1), "f32", [n, k]).permute([1, 0])
+        want = oracle.matmul(a, b).numpy().astype(np.float64)
+        bound = float((np.abs(A).astype(np.float64) @ np.abs(Bm).astype(np.float64)).max())
+        da, db = H.upload(ctx, a), H.upload(ctx, bt)
+        before = ctx.launch_count()
+        got = H.download(B.matmul(da, db)).astype(np.float64)
+        split_launches = ctx.launch_count() - before
+        assert np.abs(got - want).max() <= 2e-5 * bound, (m, k, n)
+        monkeypatch.setenv("NX_CUDA_X3_NO_SPLIT", "1")
+        before = ctx.launch_count()
+        chain = H.download(B.matmul(da, db)).astype(np.float64)
+        chain_launches = ctx.launch_count() - before
+        monkeypatch.delenv("NX_CUDA_X3_NO_SPLIT")
+        assert chain_launches == 3 and split_launches > chain_launches, (m, k, n)   # + the fold of the partials
+        assert np.abs(got - chain).max() <= 2e-6 * bound, (m, k, n)
+    Ai = A.copy()
+    Ai[3, 9] = -np.inf
+    gi = H.download(B.matmul(H.upload(ctx, H.HostView(Ai.reshape(-1), "f32", [m, k])), H.upload(ctx, b)))
+    wi = oracle.matmul(H.HostView(Ai.reshape(-1), "f32", [m, k]), b).numpy()
+    assert np.array_equal(np.isinf(gi), np.isinf(wi)) and np.array_equal(np.isnan(gi), np.isnan(wi))
+    assert np.array_equal(np.sign(gi[3]), np.sign(wi[3]))
