@@ -1,6 +1,6 @@
 """GPU parity of the fft family against the oracle through the C
 ABI: fft / ifft / rfft / irfft, unnormalised, any length (powers of two in shared memory, longer
-ones by global passes, every other length by Bluestein's chirp-z), one and several axes,
+ones by the four-step route, every other length by Bluestein's chirp-z), one and several axes,
 strided inputs, explicit irfft sizes. Both sides compute in double, so the tolerance is a small
 multiple of the OUTPUT type's epsilon relative to the largest output magnitude: 1e-5 for c32 /
 f32 results (the north star's reduction bound), 1e-11 for c64 / f64.
@@ -63,7 +63,7 @@ def test_fft_strided_views(ctx, oracle, dt):
 
 
 def test_fft_long_lines_match_reference(ctx, oracle):
-    """Lengths beyond the shared-memory core (global passes) and a long Bluestein line; the
+    """Lengths beyond the shared-memory core (four-step route) and a long Bluestein line; the
     oracle here must be the reference binary (the O(n^2) restatement would take minutes)."""
     if oracle.__name__.endswith("nxo"):
         pytest.skip("reference binary not available")
