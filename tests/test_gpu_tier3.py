@@ -141,3 +141,22 @@ def test_svd_cluster_teams(ctx, dt, monkeypatch):
             assert np.abs(u[..., :, : s.shape[-1]] @ (s[..., :, None] * vh[..., : s.shape[-1], :]) - a).max() <= 30 * tol * want.max(), (name, width)
             assert np.abs(np.swapaxes(u, -1, -2) @ u - np.eye(u.shape[-1])).max() <= 30 * tol, (name, width)
             assert np.abs(vh @ np.swapaxes(vh, -1, -2) - np.eye(vh.shape[-2])).max() <= 30 * tol, (name, width)
+
+
+def test_eig_more_columns_than_threads(ctx):
+    """The left Givens pass is a wavefront in which a thread owns the columns tid, tid + 512, ...
+    (nxc_linalg3.cuh): matrices wider than the CTA make every thread publish and await across its
+    second and third columns. Eigenvalue sets against numpy, eigenvector residual."""
+    rng = np.random.default_rng(62)
+    for n in (600, 1100):
+        a = rng.standard_normal((n, n))
+        w = H.download(B.eigvals(H.upload(ctx, H.HostView.from_array(a, "f64"))))
+        want = np.linalg.eigvals(a)
+        assert w.shape == want.shape
+        worst = max(np.min(np.abs(w - x)) for x in want)
+        assert worst <= 1e-9 * np.abs(want).max(), n
+    n = 600
+    a = rng.standard_normal((n, n)).astype(np.float32)
+    w, v = B.eig(H.upload(ctx, H.HostView.from_array(a, "f32")))
+    w, v = H.download(w), H.download(v)
+    assert np.abs(a.astype(np.complex128) @ v - v * w[None, :]).max() <= 1e-10 * n * np.abs(a).max()
