@@ -9,7 +9,12 @@ pull-backs), then the optimizer as Vega writes it (packages/vega/lib/vega.ml:813
 as the example uses, or AdamW). Data parallelism as `Rune.pmap2` defines it
 (packages/rune/lib/jit.ml:181-190): parameters replicated, the batch sharded on axis 0, gradients
 averaged across ranks -- here by bucketed NCCL all-reduces on the communication stream that start
-as the backward pass finishes each bucket (raven_b200.sharded.FlatBucketReducer).
+as the backward pass finishes each bucket (raven_b200.sharded.FlatBucketReducer). The default
+bucket (512 MB) holds all of GPT-2 small's gradient: measured at N = 2 (tools/dp_overlap_probe.py,
+profiles/dp_overlap_r02_n2.json) the launch-bound 4 x 64 step is FASTER with one exposed all-reduce
+(19.1 ms) than with 64 MB buckets racing the backward pass for the device (20.3 ms; 17.1 ms without
+any exchange), and under the bf16 sandwich every leaf becomes final only when the casts at the top
+of the step are pulled back, i.e. at the very end, so there is nothing to overlap with.
 
 One backend call per primitive, a fresh output per call, nothing fused. The whole step is a few
 thousand launches, so by default it is CAPTURED once (Context.capture) and replayed; parameters
@@ -145,7 +150,7 @@ class Trainer:
     """Persistent parameters (+ optimizer state) and one training step over them."""
 
     def __init__(self, B, ctx, cfg, batch, seq, opt="sgd", lr=1e-4, compute=None, comm=None, seed=0,
-                 bucket_mb=64, host_params=None):
+                 bucket_mb=512, host_params=None):
         from raven_b200 import dtype as D
         self.B, self.ctx, self.cfg, self.comm = B, ctx, cfg, comm
         self.batch, self.seq, self.opt, self.lr = batch, seq, opt, lr
@@ -249,13 +254,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--tiny", action="store_true")
-    ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--bucket-mb", type=int, default=512)
     args = ap.parse_args()
     print(json.dumps(run(args.batch, args.seq, args.dtype, args.opt, args.steps, args.warmup, args.eager, args.tiny,
                          args.bucket_mb)))
 
 
-def run(batch, seq, dtype="f32", opt="sgd", steps=10, warmup=3, eager=False, tiny=False, bucket_mb=64,
+def run(batch, seq, dtype="f32", opt="sgd", steps=10, warmup=3, eager=False, tiny=False, bucket_mb=512,
         ctx=None, comm=None, stream=None):
     """Times the step on this process's GPU (and its peers under torchrun). Returns the record;
     only rank 0's is meaningful for printing. `ctx` / `comm` / `stream`: reuse bench.py's."""
