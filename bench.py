@@ -597,7 +597,7 @@ def main():
             B.to_host_async(r, dst)
         return got
 
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     # W untimed steps first, like the device-timed loop: the first pipelined steps grow the
     # stream-ordered pool (a read-back still owns its buffer when the next step allocates), and a
     # pool growth of 1 GiB costs 100+ ms of driver time
