@@ -369,6 +369,16 @@ nxc_fold_lane_kernel(const typename P::S *__restrict__ in, typename P::SO *__res
           nxc_step_many<P, UL>(acc[j], col, r, TY);
         }
       }
+      // a few rows left (or a few rows in all: the sum over a batch of 4 after a batched matmul): four in flight
+      for (; r + 3 * TY < r1; r += 4 * TY) {
+        S v[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; u++) nxc_load_vec<S, VEC>(p + (r + u * TY) * rs, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int j = 0; j < VEC; j++) P::step(acc[j], v[u][j], r + u * TY);
+      }
       for (; r < r1; r += TY) {
         S v[VEC];
         nxc_load_vec<S, VEC>(p + r * rs, v);
@@ -557,7 +567,13 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
     a.small = small;
     const int64_t lane_items = (a.C + vec - 1) / vec;
     int txl = nxc_log2_ceil(lane_items);
-    if (txl > 5) txl = 5;  // 32 threads x 16 B = one 512-byte row segment per warp
+    // 32 threads x 16 B = one 512-byte row segment per warp and 8 row-walkers per lane -- unless there are only a
+    // few rows (a [4, 768, 3072] batch sum ran at 1.2 TB/s with half of every CTA idle and a shared-memory
+    // merge for 4 values): then fewer walkers, four rows each, and wider CTAs
+    int ty_log2 = 3;
+    while (ty_log2 > 0 && ((int64_t)4 << ty_log2) > p.R) ty_log2--;
+    const int txl_cap = 8 - ty_log2;  // NXC_FOLD_THREADS = 256
+    if (txl > txl_cap) txl = txl_cap;
     a.tx_log2 = txl;
     const int TX = 1 << txl, TY = NXC_FOLD_THREADS >> txl;
     a.lane_tiles = (lane_items + TX - 1) / TX;
