@@ -581,7 +581,10 @@ nxc_status nxc_fold_launch(nxc_ctx *ctx, const NxcFoldPlan &p) {
     const int64_t bx = a.lane_tiles * kother;
     int64_t S_ = 1;
     const int64_t target_blocks = (int64_t)ctx->sm_count * occ_lane;
-    if (bx < target_blocks) {
+    // (a few MB in all: a second kernel to merge row splits costs more than the few CTAs of one pass take --
+    // the bias-gradient sums of a training step, [256, 768] -> [768], were two 4 us launches each)
+    const bool tiny = (double)p.R * (double)p.O * (double)sizeof(S) <= 4.0 * 1048576.0;
+    if (bx < target_blocks && !tiny) {
       S_ = target_blocks / bx;  // round down: one wave
       const int64_t max_s = (p.R + (int64_t)TY * NxcFoldG<P>::v - 1) / ((int64_t)TY * NxcFoldG<P>::v);  // >= one unrolled pass per walker
       if (S_ > max_s) S_ = max_s;
