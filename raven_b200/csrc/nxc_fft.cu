@@ -447,12 +447,14 @@ static nxc_status nxc_fft_lines_launch(nxc_ctx *ctx, NxcFftCore c, const NxcFftG
       c.mode == NXC_FFT_MODE_LINE ? nxc_fft_lines_kernel<NXC_FFT_MODE_LINE>
                                   : (c.mode == NXC_FFT_MODE_COLS ? nxc_fft_lines_kernel<NXC_FFT_MODE_COLS>
                                                                  : nxc_fft_lines_kernel<NXC_FFT_MODE_ROWS>);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[c.mode]) {
+  // per device, not per process: a flag remembered across contexts would skip the second device of a process
+  static bool attr_set[3][64] = {};
+  const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+  if (!attr_set[c.mode][dev] || ctx->device >= 64) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * NXC_FFT_SMEM_MAX * sizeof(double2) + 16 * 256));
     if (e != cudaSuccess) { nxc_free(ctx, tw); return nxc_cuda_fail(ctx, e, "fft attribute"); }
-    attr_set[c.mode] = true;
+    attr_set[c.mode][dev] = true;
   }
   const int64_t ctas = (c.n_lines + c.lpc - 1) / c.lpc;
   if (ctas > 0x7FFFFFFF) { nxc_free(ctx, tw); return NXC_ERR_SHAPE; }  // > 2^31 CTAs: beyond any device's memory

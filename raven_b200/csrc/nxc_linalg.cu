@@ -918,12 +918,10 @@ static nxc_status nxc_qr_blocked(nxc_ctx *ctx, const nxc_tensor *w, const nxc_te
   // panels whose rows fit the cluster's shared memory (m - j0 <= 12800 f32 / 6400 f64) run there
   const bool use_cluster = !(getenv("NX_CUDA_QR_CLUSTER") && atoi(getenv("NX_CUDA_QR_CLUSTER")) == 0);
   const bool force_cluster = getenv("NX_CUDA_QR_CLUSTER") && atoi(getenv("NX_CUDA_QR_CLUSTER")) == 1;
-  static bool attr_set[2] = {false, false};
-  if (!s && use_cluster && !attr_set[sizeof(T) == 8]) {
+  if (!s && use_cluster) {  // once per call: the attribute belongs to the device, a process may drive several
     cudaError_t e = cudaFuncSetAttribute(nxc_qr_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)NXC_QR_PANEL_SMEM_MAX);
     if (e != cudaSuccess) s = nxc_cuda_fail(ctx, e, "qr panel attribute");
-    attr_set[sizeof(T) == 8] = true;
   }
   for (int64_t p = 0; p < npanels && !s; p++) {
     const int64_t j0 = p * NXC_QR_NB;
